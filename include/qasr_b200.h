@@ -1,0 +1,140 @@
+/* qasr_b200 -- C ABI of the B200-native log-mel frontend + Qwen3-ASR audio-encoder backend.
+ *
+ * This is the drop-in boundary for the encoder-backend slot of jaaacki/qwen3-asr
+ * (reference src/server.py).  The reference binds its two existing backends from Python:
+ *   - TRT slot : loader src/server.py:237-251, dispatch src/server.py:873-893
+ *   - ONNX slot: loader src/server.py:461-475, dispatch src/server.py:895-914
+ * and both replace one call: encoder.forward(input_features) -> hidden states.  The real module
+ * behind that call is m.model.thinker.audio_tower, whose forward is
+ * Qwen3OmniMoeAudioEncoder.forward(input_features[128, sum T], feature_lens[B])
+ * (transformers modeling_qwen3_omni_moe.py:698-766), fed by WhisperFeatureExtractor
+ * (feature_extraction_whisper.py:135-164, 189-342).  Each entry point below names the piece of
+ * that interface it replaces.  INTEGRATION.md shows the ctypes binding and the server.py patch.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; qasr_last_error() then holds a
+ *     message (thread-local).  There is no CPU fallback inside the library.
+ *   - device pointers are plain CUDA device addresses on the handle's device (torch tensors are
+ *     passed as tensor.data_ptr()); "stream" is a cudaStream_t passed as void* (0 = default
+ *     stream; pass torch.cuda.current_stream().cuda_stream).  Work is enqueued on that stream and
+ *     the call returns without synchronising, except the *_host entry points, which synchronise
+ *     the stream before returning because they hand back host data.
+ *   - a handle may be used by one host thread at a time (the reference has exactly one inference
+ *     thread, src/server.py:45-48).
+ */
+#ifndef QASR_B200_H_
+#define QASR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QASR_ABI_VERSION 1
+
+typedef struct qasr_handle_s* qasr_handle_t;
+
+/* dtypes for qasr_set_weight / qasr_encode */
+#define QASR_F32 0
+#define QASR_BF16 1
+#define QASR_F16 2
+
+/* Fields of thinker_config.audio_config (vllm transformers_utils/configs/qwen3_asr.py:27-130);
+ * values per checkpoint in SURVEY.md appendix A.1.  All run-time, none compiled in. */
+typedef struct qasr_config_s {
+  int32_t d_model;              /* 1024 (1.7B) / 896 (0.6B) */
+  int32_t encoder_layers;       /* 24 / 18 */
+  int32_t encoder_attention_heads; /* 16 / 14 (head_dim must be 64) */
+  int32_t encoder_ffn_dim;      /* 4096 / 3584 */
+  int32_t output_dim;           /* 2048 / 1024 */
+  int32_t n_window;             /* 50  -> 100-frame conv chunks (must be 50) */
+  int32_t n_window_infer;       /* 800 -> 104-token attention windows */
+  int32_t downsample_hidden_size; /* 480 (must be 480) */
+  int32_t num_mel_bins;         /* 128 (must be 128) */
+  int32_t max_source_positions; /* 1500 */
+  /* capacity of one internal micro-batch; larger requests are split (exactly) into several.
+   * 0 = defaults (1024 chunks = 1024 audio-seconds, 13312 tokens) */
+  int32_t max_chunks;
+  int32_t max_tokens;
+  int32_t flags;                /* reserved, must be 0 */
+} qasr_config_t;
+
+int qasr_abi_version(void);
+const char* qasr_last_error(void);
+
+/* Create a backend instance on CUDA device `device` (replaces _try_load_trt_encoder /
+ * _try_load_onnx_encoder, src/server.py:237-251, 461-475). */
+int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out);
+
+/* Hand over one parameter of the audio tower by its state_dict name without the
+ * "thinker.audio_tower." prefix (names and shapes: SURVEY.md appendix A.5), e.g.
+ * "layers.3.self_attn.q_proj.weight".  `data` may be a host or a device pointer; the library
+ * copies.  Optional extra name: "positional_embedding" [>=13, d_model] overrides the internally
+ * generated sinusoid table (modeling_qwen3_omni_moe.py:88-106). */
+int qasr_set_weight(qasr_handle_t h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
+
+/* Pack weights for the kernels (fused QKV, conv weights to [out][tap][in], conv_out K-axis
+ * permuted from c*16+f to f*480+c), upload, allocate the workspace.  Must be called once after
+ * all qasr_set_weight calls and before any encode. */
+int qasr_finalize(qasr_handle_t h);
+
+/* Device bytes held by the handle (weights + workspace). */
+size_t qasr_workspace_bytes(qasr_handle_t h);
+
+/* Token count the encoder emits for a clip of `feature_len` mel frames
+ * (_get_feat_extract_output_lengths, modeling_qwen3_omni_moe.py:145-153). */
+int64_t qasr_token_len(int64_t feature_len);
+
+/* Log-mel of n_clips mono 16 kHz float32 clips packed back to back on the device
+ * (replaces WhisperFeatureExtractor._torch_extract_fbank_features per clip, standalone semantics).
+ *   pcm_dev            float32, clip i = samples [clip_offsets[i], clip_offsets[i+1])  (host int64 [n_clips+1])
+ *   mel_out_dev        float32 [128, mel_ld], clip i occupies columns [sum_{j<i} T_j, +T_i), T_i = N_i / 160
+ *   feature_lens_out   host int64 [n_clips] (may be NULL)
+ * Every clip needs more than 200 samples (as torch.stft's reflect padding does). */
+int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, float* mel_out_dev,
+                int64_t mel_ld, int64_t* feature_lens_out, void* stream);
+
+/* Audio-tower forward (replaces audio_tower.forward / the patched encoder.forward of
+ * src/server.py:873-914).
+ *   mel_dev            [128, mel_ld] packed features, dtype QASR_F32 or QASR_BF16; clip i occupies
+ *                      columns [sum_{j<i} feature_lens[j], +feature_lens[i])
+ *   feature_lens       host int64 [n_clips]
+ *   out_dev            bf16 [sum tokens, output_dim], clip-major
+ *   token_lens_out     host int64 [n_clips] (may be NULL) */
+int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
+                void* out_dev, int64_t* token_lens_out, void* stream);
+
+/* Fused PCM -> log-mel -> encoder on the device (the mel stays in the handle's workspace). */
+int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, void* out_dev,
+                    int64_t* token_lens_out, void* stream);
+
+/* Same, end to end with HOST buffers: copies pcm_host (pinned memory recommended) to the device,
+ * encodes, copies the bf16 hidden states back into out_host and synchronises `stream`.
+ *   out_host           bf16 [sum tokens, output_dim]; out_capacity_tokens bounds the copy. */
+int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream);
+
+/* Log-mel end to end with host buffers (float32 [128, sum T] out). */
+int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
+                     int64_t* feature_lens_out, void* stream);
+
+void qasr_destroy(qasr_handle_t h);
+
+/* ---- test / bring-up hooks (not part of the serving path) ---------------------------------- */
+/* Copy a named intermediate of the LAST encode call to the host (synchronises the device).
+ * names: "act1","act2","act3","embed","mel".  Returns the number of bytes copied in *nbytes. */
+int qasr_debug_read(qasr_handle_t h, const char* name, void* dst_host, size_t capacity, size_t* nbytes);
+/* D[M,N] = act(A[M,K] * B[N,K]^T + bias) (+ residual) through the encoder's tcgen05 GEMM
+ * (impl 0) or the SIMT checker (impl 1).  All pointers are device pointers, A/B/D/residual bf16,
+ * bias float32 or NULL; act: 0 none, 1 GELU. */
+int qasr_debug_gemm(const void* a, const void* b, const float* bias, const void* residual, void* d, int m, int n, int k, int act,
+                    int impl, void* stream);
+int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int d, void* stream);
+int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QASR_B200_H_ */

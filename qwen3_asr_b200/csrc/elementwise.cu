@@ -1,0 +1,331 @@
+// conv1 (1 -> C channels, 3x3 stride 2, +bias, exact GELU), LayerNorm and the windowed
+// non-causal multi-head attention of the audio encoder.  Restates
+// transformers/models/qwen3_omni_moe/modeling_qwen3_omni_moe.py: conv2d1 :649,730; LayerNorm :576,580,647;
+// attention :496-565 / eager definition :471-493 with the per-window block-diagonal structure of :676-693.
+#include "kernels.h"
+#include "common.cuh"
+
+namespace qasr {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// conv1.  Output layout act1[(chunk*52 + col)][h = 0..63][c], col 0 and 51 are the zero columns the
+// implicit-GEMM conv2 reads as padding, col 1 + w holds output column w.  One CTA = one chunk x 13
+// output-column slots; one thread = two adjacent channels (bf16x2 stores, 128 B per warp).
+// ---------------------------------------------------------------------------------------------
+constexpr int C1_COLS = 13;                    // column slots per CTA (52 / 4)
+constexpr int C1_TILE_W = 2 * C1_COLS + 1;     // mel frames needed: 27
+constexpr int C1_TILE_H = 130;                 // mel bins -1 .. 128
+
+template <typename MelT>
+__device__ __forceinline__ float mel_load(const MelT* p);
+template <>
+__device__ __forceinline__ float mel_load<float>(const float* p) { return bf16_round(__ldg(p)); }  // the .to(bf16) cast
+template <>
+__device__ __forceinline__ float mel_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename MelT>
+__global__ void __launch_bounds__(256) conv1_kernel(const MelT* __restrict__ mel, long long ld, const ChunkDesc* __restrict__ chunks,
+                                                    const float* __restrict__ w, const float* __restrict__ bias, int channels,
+                                                    __nv_bfloat16* __restrict__ act1) {
+  __shared__ float tile[C1_TILE_H][C1_TILE_W + 1];
+  const int chunk = blockIdx.x;
+  const int slot0 = blockIdx.y * C1_COLS;  // first column slot (0..51) of this CTA
+  const ChunkDesc cd = chunks[chunk];
+  const int tid = threadIdx.x;
+
+  // mel frames f = 2*(slot-1) - 1 + j for the slots of this CTA: f0 = 2*slot0 - 3
+  const int f0 = 2 * slot0 - 3;
+  for (int i = tid; i < C1_TILE_H * C1_TILE_W; i += 256) {
+    const int r = i / C1_TILE_W, cc = i - r * C1_TILE_W;
+    const int bin = r - 1, f = f0 + cc;
+    float v = 0.f;
+    if (bin >= 0 && bin < 128 && f >= 0 && f < cd.valid) v = mel_load<MelT>(mel + bin * ld + cd.mel_col0 + f);
+    tile[r][cc] = v;
+  }
+  __syncthreads();
+
+  const int c0 = 2 * tid;
+  if (c0 >= channels) return;
+  float wa[9], wb[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) { wa[t] = w[c0 * 9 + t]; wb[t] = w[(c0 + 1) * 9 + t]; }
+  const float ba = bias[c0], bb = bias[c0 + 1];
+
+  for (int s = 0; s < C1_COLS; ++s) {
+    const int slot = slot0 + s;
+    const int ow = slot - 1;  // output column of the chunk; slot 0 / 51 are padding
+    const bool live = ow >= 0 && ow < cd.w1;
+    __nv_bfloat16* dst = act1 + ((static_cast<long long>(chunk) * ACT1_PITCH + slot) * ACT1_H) * channels + c0;
+    if (!live) {
+      for (int h = 0; h < ACT1_H; ++h) *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(h) * channels) = 0u;
+      continue;
+    }
+    const int cc = 2 * s;  // tile column of frame 2*ow - 1
+#pragma unroll 4
+    for (int h = 0; h < ACT1_H; ++h) {
+      float xa = ba, xb = bb;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float x = tile[2 * h + kh][cc + kw];
+          xa = fmaf(wa[kh * 3 + kw], x, xa);
+          xb = fmaf(wb[kh * 3 + kw], x, xb);
+        }
+      const float ya = gelu_erf(bf16_round(xa)), yb = gelu_erf(bf16_round(xb));
+      *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(h) * channels) = pack_bf16x2(ya, yb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last dim, one warp per row, fp32 statistics (two-pass in registers).
+// ---------------------------------------------------------------------------------------------
+template <int NV>  // NV = ceil(d / 256): 8-element vectors per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows,
+                                                        int d, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + static_cast<long long>(row) * d;
+  float v[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    if (col < d) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + col);
+      float2 t;
+      t = unpack_bf16x2(u.x); v[i][0] = t.x; v[i][1] = t.y;
+      t = unpack_bf16x2(u.y); v[i][2] = t.x; v[i][3] = t.y;
+      t = unpack_bf16x2(u.z); v[i][4] = t.x; v[i][5] = t.y;
+      t = unpack_bf16x2(u.w); v[i][6] = t.x; v[i][7] = t.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; sq = fmaf(t, t, sq); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+  __nv_bfloat16* orow = out + static_cast<long long>(row) * d;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    if (col < d) {
+      float g[8], b[8];
+      *reinterpret_cast<float4*>(g) = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      *reinterpret_cast<float4*>(g + 4) = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+      *reinterpret_cast<float4*>(b) = __ldg(reinterpret_cast<const float4*>(beta + col));
+      *reinterpret_cast<float4*>(b + 4) = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      uint4 u;
+      u.x = pack_bf16x2(y[0], y[1]); u.y = pack_bf16x2(y[2], y[3]);
+      u.z = pack_bf16x2(y[4], y[5]); u.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(orow + col) = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Windowed attention.  One CTA = one (window, head); K and V of the whole window live in shared
+// memory (window <= 104 tokens in both checkpoints, any length up to kMaxWin supported), each warp
+// owns 16-query row tiles and runs an online-softmax loop over 16-key blocks with
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  FLOPs here are ~1% of the encoder; the point of the
+// kernel is zero HBM round trips: packed QKV is read once, O written once.
+// ---------------------------------------------------------------------------------------------
+constexpr int HD = 64;
+constexpr int KV_STRIDE = 72;  // bf16 elements per smem row (144 B): conflict-free fragment + ldmatrix access
+constexpr int ATT_WARPS = 4;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                          __nv_bfloat16* __restrict__ out,
+                                                                          const int2* __restrict__ win, int d, float scale_log2e) {
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int2 wd = win[blockIdx.x];
+  const int start = wd.x, wl = wd.y;
+  const int head = blockIdx.y;
+  const int wl16 = (wl + 15) & ~15;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  __nv_bfloat16* sV = sK + wl16 * KV_STRIDE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long ldq = 3LL * d;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(start) * ldq + head * HD;
+
+  // stage K, V (rows >= wl zero-filled so masked P = 0 never meets garbage)
+  for (int i = tid; i < wl16 * 8; i += ATT_WARPS * 32) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 k = make_uint4(0, 0, 0, 0), v = make_uint4(0, 0, 0, 0);
+    if (r < wl) {
+      k = *reinterpret_cast<const uint4*>(base + r * ldq + d + c);
+      v = *reinterpret_cast<const uint4*>(base + r * ldq + 2 * d + c);
+    }
+    *reinterpret_cast<uint4*>(sK + r * KV_STRIDE + c) = k;
+    *reinterpret_cast<uint4*>(sV + r * KV_STRIDE + c) = v;
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  for (int qt = warp; qt * 16 < wl; qt += ATT_WARPS) {
+    const int r0 = qt * 16 + g, r1 = r0 + 8;
+    // Q fragments for the 4 k16 steps over head_dim
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      qa[ks][0] = r0 < wl ? *reinterpret_cast<const uint32_t*>(base + r0 * ldq + c) : 0u;
+      qa[ks][1] = r1 < wl ? *reinterpret_cast<const uint32_t*>(base + r1 * ldq + c) : 0u;
+      qa[ks][2] = r0 < wl ? *reinterpret_cast<const uint32_t*>(base + r0 * ldq + c + 8) : 0u;
+      qa[ks][3] = r1 < wl ? *reinterpret_cast<const uint32_t*>(base + r1 * ldq + c + 8) : 0u;
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int kb = 0; kb < wl16; kb += 16) {
+      float s[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const __nv_bfloat16* krow = sK + (kb + nt * 8 + g) * KV_STRIDE + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+          mma_bf16_16816(s[nt], qa[ks], b0, b1);
+        }
+      }
+      // scale (log2 domain) + mask keys beyond the window
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int key = kb + nt * 8 + 2 * t;
+        s[nt][0] = key < wl ? s[nt][0] * scale_log2e : -INFINITY;
+        s[nt][1] = key + 1 < wl ? s[nt][1] * scale_log2e : -INFINITY;
+        s[nt][2] = key < wl ? s[nt][2] * scale_log2e : -INFINITY;
+        s[nt][3] = key + 1 < wl ? s[nt][3] * scale_log2e : -INFINITY;
+        bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+        bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);  // finite: every block holds >= 1 live key
+      const float corr0 = exp2f(m0 - mn0), corr1 = exp2f(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      uint32_t pa[4];
+      float ps0 = 0.f, ps1 = 0.f;
+      {
+        const float p00 = exp2f(s[0][0] - mn0), p01 = exp2f(s[0][1] - mn0);
+        const float p02 = exp2f(s[0][2] - mn1), p03 = exp2f(s[0][3] - mn1);
+        const float p10 = exp2f(s[1][0] - mn0), p11 = exp2f(s[1][1] - mn0);
+        const float p12 = exp2f(s[1][2] - mn1), p13 = exp2f(s[1][3] - mn1);
+        ps0 = p00 + p01 + p10 + p11;
+        ps1 = p02 + p03 + p12 + p13;
+        pa[0] = pack_bf16x2(p00, p01);
+        pa[1] = pack_bf16x2(p02, p03);
+        pa[2] = pack_bf16x2(p10, p11);
+        pa[3] = pack_bf16x2(p12, p13);
+      }
+      l0 = l0 * corr0 + ps0;
+      l1 = l1 * corr1 + ps1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] *= corr0; o[i][1] *= corr0; o[i][2] *= corr1; o[i][3] *= corr1; }
+      // O += P V: V^T fragments through ldmatrix.trans; one x4 covers two 8-wide dim tiles
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        // matrices: (keys kb..+7, dims 16dp..+7), (keys kb+8..+15, same dims), then the same for dims 16dp+8..+15
+        const int mi = lane >> 3, ri = lane & 7;
+        const __nv_bfloat16* vrow = sV + (kb + (mi & 1) * 8 + ri) * KV_STRIDE + dp * 16 + (mi >> 1) * 8;
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, vrow);
+        mma_bf16_16816(o[2 * dp], pa, vb[0], vb[1]);
+        mma_bf16_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    __nv_bfloat16* ob = out + static_cast<long long>(start) * d + head * HD + 2 * t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (r0 < wl) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * d + i * 8) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+      if (r1 < wl) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * d + i * 8) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, const ChunkDesc* chunks, int n_chunks, const float* w,
+                         const float* bias, int channels, __nv_bfloat16* act1, cudaStream_t stream) {
+  if (n_chunks == 0) return cudaSuccess;
+  if (channels > 512 || (channels & 1)) return cudaErrorInvalidValue;
+  dim3 grid(n_chunks, ACT1_PITCH / C1_COLS);
+  if (mel_is_bf16)
+    conv1_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, channels, act1);
+  else
+    conv1_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, channels, act1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int d,
+                             float eps, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;
+  const int grid = (rows + 7) / 8;
+  const int nv = (d + 255) / 256;
+  if (nv <= 1) layernorm_kernel<1><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  else if (nv <= 2) layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  else if (nv <= 4) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  else layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len, int d,
+                                    int heads, cudaStream_t stream) {
+  if (n_win == 0) return cudaSuccess;
+  if (d != heads * HD) return cudaErrorInvalidValue;
+  const int wl16 = (max_win_len + 15) & ~15;
+  const size_t smem = static_cast<size_t>(2) * wl16 * KV_STRIDE * sizeof(__nv_bfloat16);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  const float scale_log2e = 0.125f * 1.44269504088896340736f;  // head_dim^-0.5 * log2(e)
+  dim3 grid(n_win, heads);
+  window_attention_kernel<<<grid, ATT_WARPS * 32, smem, stream>>>(qkv, out, win, d, scale_log2e);
+  return cudaGetLastError();
+}
+
+}  // namespace qasr

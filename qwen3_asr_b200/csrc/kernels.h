@@ -1,0 +1,51 @@
+// Host-callable launch wrappers for the qasr_b200 kernels.  Every wrapper enqueues on `stream`
+// and returns a cudaError_t from the launch; none of them synchronises.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "mel.cuh"
+
+namespace qasr {
+
+// ---- log-mel (mel.cu) ----------------------------------------------------------------------
+// slab table entry: one CTA = FB frames of one clip
+struct MelSlab {
+  int clip;          // clip index (per-clip max slot)
+  int frame0;        // first frame of the slab within the clip
+  int n_frames;      // valid frames in the slab (<= FB)
+  int n_samples;     // clip length in samples
+  long long pcm_off; // clip start in the packed PCM buffer
+  long long col0;    // clip start column in the packed mel
+};
+void build_mel_tables(mel::Tables* host_tables);
+cudaError_t launch_logmel(const float* pcm, const MelSlab* slabs, int n_slabs, const mel::Tables* tables,
+                          float* mel_out, long long mel_ld, unsigned int* clip_max, cudaStream_t stream);
+// clip_cols: [n_clips + 1] column offsets of each clip in the packed mel
+cudaError_t launch_logmel_finish(float* mel_out, long long mel_ld, const long long* clip_cols, int n_clips,
+                                 const unsigned int* clip_max, cudaStream_t stream);
+
+// ---- conv1 (elementwise.cu) ------------------------------------------------------------------
+struct ChunkDesc {
+  long long mel_col0;  // first mel column of the chunk in the packed mel
+  int valid;           // valid mel frames in the chunk
+  int w1;              // valid conv1 output columns (conv_len(padded frames))
+};
+constexpr int ACT1_PITCH = 52;  // columns per chunk in conv1's output: [zero][50][zero]
+constexpr int ACT1_H = 64;
+cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, const ChunkDesc* chunks, int n_chunks,
+                         const float* w /*[C][9]*/, const float* bias /*[C]*/, int channels,
+                         __nv_bfloat16* act1, cudaStream_t stream);
+
+// ---- LayerNorm -------------------------------------------------------------------------------
+cudaError_t launch_layernorm(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* out,
+                             int rows, int d, float eps, cudaStream_t stream);
+
+// ---- windowed attention ----------------------------------------------------------------------
+// qkv: [tokens, 3d] (q | k | v, head h at columns h*64); out: [tokens, d]; win: [n_win] (start, len)
+cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* win, int n_win,
+                                    int max_win_len, int d, int heads, cudaStream_t stream);
+
+}  // namespace qasr

@@ -1,0 +1,347 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: D[M,N] = A[M,K] * B[N,K]^T, bf16 in, fp32 accumulate in TMEM.
+//
+// One persistent, warp-specialised kernel serves every matrix product of the audio encoder:
+//   * the Linear layers (K7, K9-K12 of SURVEY.md section 2.3): A is a row-major [M,K] activation,
+//   * the 3x3 stride-2 convolutions as implicit GEMM (K3, K4): A is gathered by TMA straight from
+//     the NHWC-like activation (a 3-D box with traversal stride 2 per filter tap, out-of-bounds
+//     rows zero-filled by the TMA unit), K = 9 taps x 512 (480 channels padded),
+//   * conv_out (K5): A is conv3's output viewed as [chunk*13, 16*480].
+// B is always an nn.Linear-style [N,K] row-major (K-major) weight.
+//
+// Roles (256 threads, 1 CTA per SM, grid = #SMs):
+//   warp 0 lane 0 : TMA producer   -- cp.async.bulk.tensor into a kStages-deep 128B-swizzled ring
+//   warp 1 lane 0 : MMA issuer     -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage
+//   warp 2        : TMEM allocator -- 512 columns = two accumulator stages
+//   warps 4..7    : epilogue       -- tcgen05.ld 32 lanes x 32b, fused bias/GELU/residual/... -> bf16
+// Pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) mbarriers, so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace qasr {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kTmemCols = 512;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+enum AMode : int { A_LINEAR = 0, A_CONV = 1 };
+
+struct GemmShape {
+  int m_tiles;      // number of 128-row tiles
+  int n_tiles;      // number of BN-column tiles
+  int num_kb;       // K / 64
+  // A_CONV only: K index kb -> (tap = kb / kb_per_tap, channel block = kb % kb_per_tap);
+  // output tile m_blk covers gt global output columns x (128 / gt) output rows.
+  int kb_per_tap;
+  int gt;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> a CUDA error the host reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+      printf("qasr tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major, dense.
+//   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
+//   [15] a_major=0 (K)  [16] b_major=0 (K)  [17,23) N>>3  [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+// Shared-memory matrix descriptor for a K-major tile stored as rows of 128 bytes with SWIZZLE_128B
+// (exactly what a TMA box with inner extent 64 bf16 and CU_TENSOR_MAP_SWIZZLE_128B writes):
+//   [0,14) start>>4  [16,30) LBO>>4 (=1, unused for swizzled K-major)  [32,46) SBO>>4 (8 rows*128B = 1024)
+//   [46,48) version=1 (sm_100)  [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // +1024: manual alignment slack
+  static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
+};
+
+template <int BN>
+constexpr int default_stages() { return BN > 192 ? 4 : (BN > 128 ? 4 : 6); }
+
+// ---------------------------------------------------------------------------------------------
+// The kernel.  Epi::operator()(row, col0, const float (&acc)[16]) consumes 16 consecutive columns
+// of one accumulator row; it does its own bounds/validity checks.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int AMODE, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape, Epi epi) {
+  using L = SmemLayout<BN, STAGES>;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
+  static_assert(2 * BN <= kTmemCols, "two accumulator stages must fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* full_bar = bars;                      // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES] MMA -> TMA
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [2] MMA -> epilogue
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = shape.m_tiles * shape.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one elected lane of each epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / shape.n_tiles;
+        const int n_blk = tile % shape.n_tiles;
+        for (int kb = 0; kb < shape.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if constexpr (AMODE == A_LINEAR) {
+            tma_load_2d(sa, &tmA, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
+          } else {
+            const int tap = kb / shape.kb_per_tap;
+            const int cb = kb - tap * shape.kb_per_tap;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            // input column = 2 * (global output column) + kw (left zero column is part of the layout),
+            // input row    = 2 * (output row) + kh - 1    (row -1 is out of bounds -> TMA zero fill)
+            tma_load_3d(sa, &tmA, cb * BLOCK_K, kh - 1, 2 * (m_blk * shape.gt) + kw, &full_bar[stage]);
+          }
+          tma_load_2d(sb, &tmB, kb * BLOCK_K, n_blk * BN, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < shape.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the 128B swizzle atom: +2 in the >>4 address field
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == shape.num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int q = warp - kEpiWarp0;  // == warp % 4: the TMEM lane quarter this warp may read
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int m_blk = tile / shape.n_tiles;
+      const int n_blk = tile % shape.n_tiles;
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld16(taddr + c, v);
+        if (c + 16 < BN) tmem_ld16(taddr + c + 16, v + 16);
+        tmem_ld_wait();
+        epi(row, n_blk * BN + c, reinterpret_cast<const float(&)[16]>(v[0]));
+        if (c + 16 < BN) epi(row, n_blk * BN + c + 16, reinterpret_cast<const float(&)[16]>(v[16]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Debug-only SIMT evaluation of the same product with the same epilogue functor (bring-up aid:
+// lets the tests tell a TMA/UMMA descriptor bug from an epilogue or layout bug).  Never used by
+// the product path unless QASR_DEBUG_SIMT=1 is set.
+// ---------------------------------------------------------------------------------------------
+struct ALoadLinear {
+  const __nv_bfloat16* a;
+  long long lda;
+  int m_valid;
+  __device__ float operator()(int m, int k) const { return m < m_valid ? __bfloat162float(a[m * lda + k]) : 0.f; }
+};
+struct ALoadConv {
+  const __nv_bfloat16* a;  // [G_in][H_in][C]
+  int g_in, h_in, c, hc;   // hc = output rows per output column
+  __device__ float operator()(int m, int k) const {
+    const int tap = k / 512, ch = k % 512;
+    if (ch >= c) return 0.f;
+    const int kh = tap / 3, kw = tap % 3;
+    const int g = m / hc, h = m % hc;
+    const int col = 2 * g + kw, row = 2 * h + kh - 1;
+    if (col < 0 || col >= g_in || row < 0 || row >= h_in) return 0.f;
+    return __bfloat162float(a[(static_cast<long long>(col) * h_in + row) * c + ch]);
+  }
+};
+
+template <class ALoad, class Epi>
+__global__ void gemm_simt_kernel(ALoad aload, const __nv_bfloat16* __restrict__ b, long long ldb, int m_rows, int n, int k, Epi epi) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int n_chunks = n / 16;
+  const int m = static_cast<int>(idx / n_chunks);
+  const int n0 = static_cast<int>(idx % n_chunks) * 16;
+  if (m >= m_rows) return;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int kk = 0; kk < k; ++kk) {
+    const float av = aload(m, kk);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = fmaf(av, __bfloat162float(b[(n0 + j) * ldb + kk]), acc[j]);
+  }
+  epi(m, n0, acc);
+}
+
+}  // namespace tc
+}  // namespace qasr
