@@ -34,6 +34,12 @@ extern "C" {
 
 #define QASR_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define QASR_API __attribute__((visibility("default")))
+#else
+#define QASR_API
+#endif
+
 typedef struct qasr_handle_s* qasr_handle_t;
 
 /* dtypes for qasr_set_weight / qasr_encode */
@@ -61,31 +67,31 @@ typedef struct qasr_config_s {
   int32_t flags;                /* reserved, must be 0 */
 } qasr_config_t;
 
-int qasr_abi_version(void);
-const char* qasr_last_error(void);
+QASR_API int qasr_abi_version(void);
+QASR_API const char* qasr_last_error(void);
 
 /* Create a backend instance on CUDA device `device` (replaces _try_load_trt_encoder /
  * _try_load_onnx_encoder, src/server.py:237-251, 461-475). */
-int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out);
+QASR_API int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out);
 
 /* Hand over one parameter of the audio tower by its state_dict name without the
  * "thinker.audio_tower." prefix (names and shapes: SURVEY.md appendix A.5), e.g.
  * "layers.3.self_attn.q_proj.weight".  `data` may be a host or a device pointer; the library
  * copies.  Optional extra name: "positional_embedding" [>=13, d_model] overrides the internally
  * generated sinusoid table (modeling_qwen3_omni_moe.py:88-106). */
-int qasr_set_weight(qasr_handle_t h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
+QASR_API int qasr_set_weight(qasr_handle_t h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
 
 /* Pack weights for the kernels (fused QKV, conv weights to [out][tap][in], conv_out K-axis
  * permuted from c*16+f to f*480+c), upload, allocate the workspace.  Must be called once after
  * all qasr_set_weight calls and before any encode. */
-int qasr_finalize(qasr_handle_t h);
+QASR_API int qasr_finalize(qasr_handle_t h);
 
 /* Device bytes held by the handle (weights + workspace). */
-size_t qasr_workspace_bytes(qasr_handle_t h);
+QASR_API size_t qasr_workspace_bytes(qasr_handle_t h);
 
 /* Token count the encoder emits for a clip of `feature_len` mel frames
  * (_get_feat_extract_output_lengths, modeling_qwen3_omni_moe.py:145-153). */
-int64_t qasr_token_len(int64_t feature_len);
+QASR_API int64_t qasr_token_len(int64_t feature_len);
 
 /* Log-mel of n_clips mono 16 kHz float32 clips packed back to back on the device
  * (replaces WhisperFeatureExtractor._torch_extract_fbank_features per clip, standalone semantics).
@@ -93,7 +99,7 @@ int64_t qasr_token_len(int64_t feature_len);
  *   mel_out_dev        float32 [128, mel_ld], clip i occupies columns [sum_{j<i} T_j, +T_i), T_i = N_i / 160
  *   feature_lens_out   host int64 [n_clips] (may be NULL)
  * Every clip needs more than 200 samples (as torch.stft's reflect padding does). */
-int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, float* mel_out_dev,
+QASR_API int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, float* mel_out_dev,
                 int64_t mel_ld, int64_t* feature_lens_out, void* stream);
 
 /* Audio-tower forward (replaces audio_tower.forward / the patched encoder.forward of
@@ -103,36 +109,47 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
  *   feature_lens       host int64 [n_clips]
  *   out_dev            bf16 [sum tokens, output_dim], clip-major
  *   token_lens_out     host int64 [n_clips] (may be NULL) */
-int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
+QASR_API int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
                 void* out_dev, int64_t* token_lens_out, void* stream);
 
 /* Fused PCM -> log-mel -> encoder on the device (the mel stays in the handle's workspace). */
-int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, void* out_dev,
+QASR_API int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, void* out_dev,
                     int64_t* token_lens_out, void* stream);
 
 /* Same, end to end with HOST buffers: copies pcm_host (pinned memory recommended) to the device,
  * encodes, copies the bf16 hidden states back into out_host and synchronises `stream`.
  *   out_host           bf16 [sum tokens, output_dim]; out_capacity_tokens bounds the copy. */
-int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+QASR_API int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                          int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream);
 
 /* Log-mel end to end with host buffers (float32 [128, sum T] out). */
-int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
+QASR_API int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
                      int64_t* feature_lens_out, void* stream);
 
-void qasr_destroy(qasr_handle_t h);
+QASR_API void qasr_destroy(qasr_handle_t h);
+
+/* ---- launch accounting and per-launch timing (measurement; bench.py's roofline figures) ------- */
+/* Number of CUDA kernels this handle has launched so far. */
+QASR_API uint64_t qasr_launch_count(qasr_handle_t h);
+/* on != 0: bracket every kernel launch with CUDA events on the launching stream (clears earlier
+ * records).  qasr_profile_read synchronises the device and returns, aggregated by kernel name in
+ * first-launch order: '\n'-separated names, summed milliseconds, summed algorithmic work (FLOPs;
+ * bytes for "logmel") and launch counts. */
+QASR_API int qasr_profile_enable(qasr_handle_t h, int on);
+QASR_API int qasr_profile_read(qasr_handle_t h, char* names, size_t names_cap, double* ms, double* work, int32_t* counts,
+                               int max_entries, int* n_entries);
 
 /* ---- test / bring-up hooks (not part of the serving path) ---------------------------------- */
 /* Copy a named intermediate of the LAST encode call to the host (synchronises the device).
  * names: "act1","act2","act3","embed","mel".  Returns the number of bytes copied in *nbytes. */
-int qasr_debug_read(qasr_handle_t h, const char* name, void* dst_host, size_t capacity, size_t* nbytes);
+QASR_API int qasr_debug_read(qasr_handle_t h, const char* name, void* dst_host, size_t capacity, size_t* nbytes);
 /* D[M,N] = act(A[M,K] * B[N,K]^T + bias) (+ residual) through the encoder's tcgen05 GEMM
  * (impl 0) or the SIMT checker (impl 1).  All pointers are device pointers, A/B/D/residual bf16,
  * bias float32 or NULL; act: 0 none, 1 GELU. */
-int qasr_debug_gemm(const void* a, const void* b, const float* bias, const void* residual, void* d, int m, int n, int k, int act,
+QASR_API int qasr_debug_gemm(const void* a, const void* b, const float* bias, const void* residual, void* d, int m, int n, int k, int act,
                     int impl, void* stream);
-int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int d, void* stream);
-int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream);
+QASR_API int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int d, void* stream);
+QASR_API int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,184 @@
+// Launchers for the tcgen05 GEMM family and TMA tensor-map construction.
+#include "gemm.h"
+
+#include <algorithm>
+#include <string>
+
+#include "epilogues.cuh"
+#include "tc_gemm.cuh"
+
+namespace qasr {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+
+}  // namespace
+
+int tmap_api_init() {
+  if (g_encode_tiled != nullptr) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_last_error(std::string("cuTensorMapEncodeTiled not available from the driver: ") + cudaGetErrorString(e));
+    return 2;
+  }
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+int make_tmap_rowmajor(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  if (tmap_api_init() != 0) return 2;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(tc::BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(2d) failed with CUresult " + std::to_string(static_cast<int>(r)) + " rows=" +
+                   std::to_string(rows) + " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld));
+    return 2;
+  }
+  return 0;
+}
+
+int make_tmap_conv(CUtensorMap* tm, const void* base, long long g_in, int h_in, int c, int hc, int gt) {
+  if (tmap_api_init() != 0) return 2;
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(h_in), static_cast<cuuint64_t>(g_in)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(c) * 2 * static_cast<cuuint64_t>(h_in)};
+  // with a traversal stride s the box extent is (elements to load) * s
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(tc::BLOCK_K), static_cast<cuuint32_t>(2 * hc), static_cast<cuuint32_t>(2 * gt)};
+  const cuuint32_t estr[3] = {1, 2, 2};
+  const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(conv) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 2;
+  }
+  return 0;
+}
+
+int pick_bn(int n) {
+  if (n % 256 == 0) return 256;
+  if (n % 128 == 0) return 128;
+  if (n % 64 == 0) return 64;
+  return 0;
+}
+
+namespace {
+
+template <int BN, int AMODE, class Epi>
+cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc::GemmShape& shape, const Epi& epi, int num_sms,
+                      cudaStream_t stream) {
+  constexpr int ST = tc::default_stages<BN>();
+  using L = tc::SmemLayout<BN, ST>;
+  auto kern = tc::gemm_tc_kernel<BN, ST, AMODE, Epi>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  if (e != cudaSuccess) return e;
+  const int tiles = shape.m_tiles * shape.n_tiles;
+  if (tiles <= 0) return cudaSuccess;
+  const int grid = std::min(tiles, num_sms);
+  kern<<<grid, tc::kThreads, L::TOTAL, stream>>>(tm_a, tm_b, shape, epi);
+  return cudaGetLastError();
+}
+
+template <class ALoad, class Epi>
+cudaError_t launch_simt(const ALoad& aload, const __nv_bfloat16* b, long long ldb, int m, int n, int k, const Epi& epi, cudaStream_t stream) {
+  const long long items = static_cast<long long>(m) * (n / 16);
+  if (items <= 0) return cudaSuccess;
+  const int threads = 128;
+  const long long blocks = (items + threads - 1) / threads;
+  tc::gemm_simt_kernel<<<static_cast<unsigned int>(blocks), threads, 0, stream>>>(aload, b, ldb, m, n, k, epi);
+  return cudaGetLastError();
+}
+
+template <class Epi>
+cudaError_t linear_dispatch(const LinearArgs& a, const Epi& epi, bool simt, int num_sms, cudaStream_t stream) {
+  if (simt) {
+    tc::ALoadLinear al{a.a, a.lda, a.m};
+    return launch_simt(al, a.b, a.ldb, a.m, a.n, a.k, epi, stream);
+  }
+  tc::GemmShape sh{};
+  sh.m_tiles = (a.m + tc::BLOCK_M - 1) / tc::BLOCK_M;
+  sh.n_tiles = a.n / a.bn;
+  sh.num_kb = a.k / tc::BLOCK_K;
+  sh.kb_per_tap = 1;
+  sh.gt = 1;
+  switch (a.bn) {
+    case 256: return launch_tc<256, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
+    case 128: return launch_tc<128, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
+    case 64: return launch_tc<64, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_t stream) {
+  if (a.m <= 0) return cudaSuccess;
+  if (a.k % tc::BLOCK_K != 0 || a.n % 16 != 0 || (!simt && (a.bn == 0 || a.n % a.bn != 0))) return cudaErrorInvalidValue;
+  switch (a.epi) {
+    case LIN_PLAIN: {
+      EpiLinear<ACT_NONE, false> e{a.out, a.bias, nullptr, a.ldo, a.m, a.n};
+      return linear_dispatch(a, e, simt, num_sms, stream);
+    }
+    case LIN_GELU: {
+      EpiLinear<ACT_GELU, false> e{a.out, a.bias, nullptr, a.ldo, a.m, a.n};
+      return linear_dispatch(a, e, simt, num_sms, stream);
+    }
+    case LIN_RESIDUAL: {
+      EpiLinear<ACT_NONE, true> e{a.out, a.bias, a.residual, a.ldo, a.m, a.n};
+      return linear_dispatch(a, e, simt, num_sms, stream);
+    }
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t gemm_conv(const ConvArgs& a, bool simt, int num_sms, cudaStream_t stream) {
+  if (a.n_chunks <= 0) return cudaSuccess;
+  if (a.c != 480 || a.hc * a.gt != tc::BLOCK_M) return cudaErrorInvalidValue;
+  EpiConv e{a.out, a.bias, a.width, a.hc, a.slots, a.max_w, a.out_pitch, a.out_off, a.n_chunks, a.c};
+  const long long g_out = static_cast<long long>(a.n_chunks) * a.slots;  // global output columns
+  if (simt) {
+    tc::ALoadConv al{a.a, static_cast<int>(a.g_in), a.h_in, a.c, a.hc};
+    return launch_simt(al, a.b, 9 * 512, static_cast<int>(g_out * a.hc), a.c, 9 * 512, e, stream);
+  }
+  tc::GemmShape sh{};
+  sh.m_tiles = static_cast<int>((g_out + a.gt - 1) / a.gt);
+  sh.n_tiles = 2;
+  sh.num_kb = 9 * 8;
+  sh.kb_per_tap = 8;
+  sh.gt = a.gt;
+  return launch_tc<240, tc::A_CONV>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+}
+
+cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStream_t stream) {
+  if (a.m <= 0) return cudaSuccess;
+  if (a.k % tc::BLOCK_K != 0 || a.d % 16 != 0) return cudaErrorInvalidValue;
+  EpiConvOut e{a.out, a.pe, a.row_token, a.tok_per_chunk, a.d, a.m};
+  if (simt) {
+    tc::ALoadLinear al{a.a, a.k, a.m};
+    return launch_simt(al, a.b, a.k, a.m, a.d, a.k, e, stream);
+  }
+  tc::GemmShape sh{};
+  sh.m_tiles = (a.m + tc::BLOCK_M - 1) / tc::BLOCK_M;
+  sh.n_tiles = a.d / a.bn;
+  sh.num_kb = a.k / tc::BLOCK_K;
+  sh.kb_per_tap = 1;
+  sh.gt = 1;
+  switch (a.bn) {
+    case 256: return launch_tc<256, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+    case 128: return launch_tc<128, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+    case 64: return launch_tc<64, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace qasr

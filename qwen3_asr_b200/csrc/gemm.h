@@ -1,0 +1,77 @@
+// Host-side launchers of the tcgen05 GEMM family (tc_gemm.cuh) and the TMA tensor-map builders.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace qasr {
+
+// Resolves cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda, so the
+// library loads -- and exports its symbols -- on a box without a driver).  0 on success.
+int tmap_api_init();
+
+// bf16 row-major [rows, cols] (leading dimension ld elements), box = box_rows x 64 columns, 128B swizzle.
+int make_tmap_rowmajor(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// bf16 activation [g_in columns][h_in rows][c channels] read by a 3x3 stride-2 convolution as
+// implicit GEMM: box = 64 channels x hc output rows x gt output columns, traversal stride 2 on
+// rows and columns.
+int make_tmap_conv(CUtensorMap* tm, const void* base, long long g_in, int h_in, int c, int hc, int gt);
+
+// Largest supported N tile (256 / 128 / 64) that divides n; 0 if none.
+int pick_bn(int n);
+
+enum LinearEpi : int { LIN_PLAIN = 0, LIN_GELU = 1, LIN_RESIDUAL = 2 };
+
+struct LinearArgs {
+  const CUtensorMap* tm_a;     // [m_cap, k] activations
+  const CUtensorMap* tm_b;     // [n, k] weight, box rows = bn
+  int bn;
+  const __nv_bfloat16* a;      // raw pointers for the SIMT checker
+  long long lda;
+  const __nv_bfloat16* b;
+  long long ldb;
+  int m, n, k;
+  int epi;                     // LinearEpi
+  __nv_bfloat16* out;
+  long long ldo;
+  const float* bias;           // [n] or nullptr
+  const __nv_bfloat16* residual;  // LIN_RESIDUAL: [m, ldo]
+};
+cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_t stream);
+
+struct ConvArgs {
+  const CUtensorMap* tm_a;     // make_tmap_conv over the input activation
+  const CUtensorMap* tm_b;     // [480, 9*512] packed weight, box rows = 240
+  const __nv_bfloat16* a;      // input activation [g_in][h_in][c]
+  long long g_in;
+  int h_in;
+  const __nv_bfloat16* b;      // [c][9*512]
+  int n_chunks;
+  int hc;                      // output rows per column (32 / 16)
+  int gt;                      // output columns per 128-row tile (4 / 8)
+  int slots;                   // output column slots per chunk (26 / 13)
+  int max_w;                   // 25 / 13
+  int out_pitch, out_off;
+  const int* width;            // [n_chunks] valid output columns
+  const float* bias;           // [c]
+  __nv_bfloat16* out;
+  int c;                       // 480
+};
+cudaError_t gemm_conv(const ConvArgs& a, bool simt, int num_sms, cudaStream_t stream);
+
+struct ConvOutArgs {
+  const CUtensorMap* tm_a;     // [chunks*13, 7680]
+  const CUtensorMap* tm_b;     // [d, 7680] (K axis permuted to f*480+c), box rows = bn
+  int bn;
+  const __nv_bfloat16* a;
+  const __nv_bfloat16* b;
+  int m, d, k;
+  const float* pe;             // [13, d]
+  const int* row_token;        // [m]
+  int tok_per_chunk;
+  __nv_bfloat16* out;          // [tokens, d]
+};
+cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStream_t stream);
+
+}  // namespace qasr

@@ -1,0 +1,984 @@
+// C ABI of the B200 log-mel + Qwen3-ASR audio-encoder backend (include/qasr_b200.h).
+//
+// Host logic only: parameter staging and packing, the per-call chunk / window / token plan
+// (restating transformers modeling_qwen3_omni_moe.py:145-153, 711-726, 745-752 on the host so the
+// device never has to sync back lengths), workspace management and kernel sequencing.  All
+// arithmetic is in the kernels (mel.cu, elementwise.cu, tc_gemm.cuh); there is no CPU fallback.
+#include "../../include/qasr_b200.h"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "kernels.h"
+
+namespace qasr {
+namespace {
+thread_local std::string g_last_error;
+}
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace qasr
+
+using namespace qasr;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+constexpr int kTokPerChunk = 13;   // tokens of a full 100-frame chunk (three stride-2 convs: 100 -> 50 -> 25 -> 13)
+constexpr int kConvC = 480;
+constexpr int kConvKPad = 9 * 512;  // 9 taps x (480 channels padded to 512)
+constexpr int kStagingSlots = 4;
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (int64_t s : shape) n *= s;
+    return n;
+  }
+};
+
+struct LinearW {
+  bf16* w = nullptr;    // [n, k]
+  float* b = nullptr;   // [n] or nullptr
+  int n = 0, k = 0, bn = 0;
+  CUtensorMap tm;
+};
+
+struct LayerW {
+  LinearW qkv, out, fc1, fc2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+
+struct Staging {
+  uint8_t* host = nullptr;
+  uint8_t* dev = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool in_flight = false;
+};
+
+struct GrowBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+inline int conv_len(int n) { return n <= 0 ? 0 : (n - 1) / 2 + 1; }
+inline int conv_len3(int n) { return conv_len(conv_len(conv_len(n))); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct qasr_handle_s {
+  qasr_config_t cfg{};
+  int device = 0;
+  int num_sms = kNumSMs;
+  bool finalized = false;
+  bool simt = false;        // QASR_DEBUG_SIMT=1: run every GEMM through the SIMT checker kernel
+  bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
+  int chunks_per_window = 8;
+  int max_chunks = 0, max_tokens = 0;
+
+  std::map<std::string, HostTensor> staged;
+  std::vector<void*> allocs;
+  size_t device_bytes = 0;
+
+  // parameters
+  float *conv1_w = nullptr, *conv1_b = nullptr;
+  bf16 *conv2_w = nullptr, *conv3_w = nullptr;
+  float *conv2_b = nullptr, *conv3_b = nullptr;
+  CUtensorMap tm_conv2_w, tm_conv3_w;
+  LinearW conv_out;  // [d, 7680], K axis permuted
+  float* pe = nullptr;
+  std::vector<LayerW> layers;
+  float *lnp_g = nullptr, *lnp_b = nullptr;
+  LinearW proj1, proj2;
+  mel::Tables* mel_tables = nullptr;
+
+  // workspace
+  bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr;
+  bf16 *x = nullptr, *hbuf = nullptr, *qkv = nullptr, *att = nullptr, *ffn = nullptr, *embed_dbg = nullptr;
+  CUtensorMap tm_act1, tm_act2, tm_act3, tm_h, tm_att, tm_ffn;
+  Staging staging[kStagingSlots];
+  int next_slot = 0;
+  GrowBuf mel_buf, pcm_buf, out_buf, clipmax_buf;
+
+  // launch accounting + optional per-launch CUDA-event timing (qasr_profile_*)
+  unsigned long long launches = 0;
+  bool profiling = false;
+  struct ProfRec { const char* name; double work; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+
+  // last-call bookkeeping for qasr_debug_read
+  int last_chunks = 0, last_tokens = 0;
+  long long last_mel_cols = 0, last_mel_ld = 0;
+};
+
+namespace {
+
+int dev_alloc(qasr_handle_s* h, void** p, size_t bytes) {
+  bytes = std::max<size_t>(bytes, 256);
+  QASR_CUDA_CHECK(cudaMalloc(p, bytes));
+  h->allocs.push_back(*p);
+  h->device_bytes += bytes;
+  return 0;
+}
+
+int grow(qasr_handle_s* h, GrowBuf* b, size_t bytes) {
+  if (bytes <= b->cap) return 0;
+  if (b->p != nullptr) {
+    QASR_CUDA_CHECK(cudaDeviceSynchronize());
+    QASR_CUDA_CHECK(cudaFree(b->p));
+    h->device_bytes -= b->cap;
+    b->p = nullptr;
+    b->cap = 0;
+  }
+  const size_t want = align_up(bytes + bytes / 4, 1 << 20);
+  QASR_CUDA_CHECK(cudaMalloc(&b->p, want));
+  b->cap = want;
+  h->device_bytes += want;
+  return 0;
+}
+
+// Acquire a staging slot with at least `bytes` of pinned host + device memory.
+int staging_acquire(qasr_handle_s* h, size_t bytes, Staging** out) {
+  Staging* s = &h->staging[h->next_slot];
+  h->next_slot = (h->next_slot + 1) % kStagingSlots;
+  if (s->ev == nullptr) QASR_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
+  if (s->in_flight) {
+    QASR_CUDA_CHECK(cudaEventSynchronize(s->ev));
+    s->in_flight = false;
+  }
+  if (bytes > s->cap) {
+    if (s->host != nullptr) QASR_CUDA_CHECK(cudaFreeHost(s->host));
+    if (s->dev != nullptr) {
+      QASR_CUDA_CHECK(cudaFree(s->dev));
+      h->device_bytes -= s->cap;
+    }
+    s->host = nullptr;
+    s->dev = nullptr;
+    s->cap = 0;
+    const size_t want = align_up(bytes + bytes / 2, 1 << 16);
+    QASR_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&s->host), want));
+    QASR_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->dev), want));
+    s->cap = want;
+    h->device_bytes += want;
+  }
+  *out = s;
+  return 0;
+}
+
+cudaEvent_t prof_event(qasr_handle_s* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// Every kernel launch of the product path goes through this: counts it and, when profiling is on,
+// brackets it with CUDA events on the launching stream.  `work` = algorithmic FLOPs (or bytes, mel).
+#define QASR_LAUNCH(h, name_, work_, stream_, expr)                       \
+  do {                                                                    \
+    cudaEvent_t _e0 = nullptr, _e1 = nullptr;                             \
+    if ((h)->profiling) {                                                 \
+      _e0 = prof_event(h);                                                \
+      _e1 = prof_event(h);                                                \
+      cudaEventRecord(_e0, (stream_));                                    \
+    }                                                                     \
+    QASR_CUDA_CHECK(expr);                                                \
+    ++(h)->launches;                                                      \
+    if ((h)->profiling) {                                                 \
+      cudaEventRecord(_e1, (stream_));                                    \
+      (h)->prof.push_back({(name_), static_cast<double>(work_), _e0, _e1}); \
+    }                                                                     \
+  } while (0)
+
+const HostTensor* find_weight(qasr_handle_s* h, const std::string& name) {
+  auto it = h->staged.find(name);
+  return it == h->staged.end() ? nullptr : &it->second;
+}
+
+int need_weight(qasr_handle_s* h, const std::string& name, std::initializer_list<int64_t> shape, const HostTensor** out) {
+  const HostTensor* t = find_weight(h, name);
+  if (t == nullptr) {
+    set_last_error("missing weight: " + name);
+    return 1;
+  }
+  int64_t want = 1;
+  for (int64_t s : shape) want *= s;
+  if (t->numel() != want) {
+    set_last_error("weight " + name + " has " + std::to_string(t->numel()) + " elements, expected " + std::to_string(want));
+    return 1;
+  }
+  *out = t;
+  return 0;
+}
+
+int upload_f32(qasr_handle_s* h, const float* src, size_t n, float** dst) {
+  if (dev_alloc(h, reinterpret_cast<void**>(dst), n * sizeof(float)) != 0) return 2;
+  QASR_CUDA_CHECK(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int upload_bf16(qasr_handle_s* h, const float* src, size_t n, bf16** dst) {
+  std::vector<bf16> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(src[i]);
+  if (dev_alloc(h, reinterpret_cast<void**>(dst), n * sizeof(bf16)) != 0) return 2;
+  QASR_CUDA_CHECK(cudaMemcpy(*dst, tmp.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// nn.Linear [n, k] (+ bias) -> device bf16 weight, f32 bias, TMA map with box rows = bn
+int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, LinearW* out) {
+  out->n = n;
+  out->k = k;
+  out->bn = pick_bn(n);
+  QASR_REQUIRE(out->bn != 0, "linear output width " + std::to_string(n) + " is not a multiple of 64");
+  QASR_REQUIRE(k % 64 == 0, "linear input width " + std::to_string(k) + " is not a multiple of 64");
+  if (upload_bf16(h, w, static_cast<size_t>(n) * k, &out->w) != 0) return 2;
+  if (b != nullptr && upload_f32(h, b, n, &out->b) != 0) return 2;
+  return make_tmap_rowmajor(&out->tm, out->w, n, k, k, out->bn);
+}
+
+int load_linear(qasr_handle_s* h, const std::string& prefix, int n, int k, bool bias, LinearW* out) {
+  const HostTensor *w = nullptr, *b = nullptr;
+  if (need_weight(h, prefix + ".weight", {n, k}, &w) != 0) return 1;
+  if (bias && need_weight(h, prefix + ".bias", {n}, &b) != 0) return 1;
+  return make_linear(h, w->data.data(), bias ? b->data.data() : nullptr, n, k, out);
+}
+
+int load_vec(qasr_handle_s* h, const std::string& name, int n, float** out) {
+  const HostTensor* t = nullptr;
+  if (need_weight(h, name, {n}, &t) != 0) return 1;
+  return upload_f32(h, t->data.data(), n, out);
+}
+
+// conv weight OIHW [480, 480, 3, 3] -> [o][tap = kh*3+kw][512 (i, zero padded)]
+int load_conv(qasr_handle_s* h, const std::string& prefix, bf16** w_out, float** b_out, CUtensorMap* tm) {
+  const HostTensor *w = nullptr, *b = nullptr;
+  if (need_weight(h, prefix + ".weight", {kConvC, kConvC, 3, 3}, &w) != 0) return 1;
+  if (need_weight(h, prefix + ".bias", {kConvC}, &b) != 0) return 1;
+  std::vector<float> packed(static_cast<size_t>(kConvC) * kConvKPad, 0.f);
+  for (int o = 0; o < kConvC; ++o)
+    for (int i = 0; i < kConvC; ++i)
+      for (int t = 0; t < 9; ++t) packed[static_cast<size_t>(o) * kConvKPad + t * 512 + i] = w->data[(static_cast<size_t>(o) * kConvC + i) * 9 + t];
+  if (upload_bf16(h, packed.data(), packed.size(), w_out) != 0) return 2;
+  if (upload_f32(h, b->data.data(), kConvC, b_out) != 0) return 2;
+  return make_tmap_rowmajor(tm, *w_out, kConvC, kConvKPad, kConvKPad, 240);
+}
+
+struct Unit {  // one attention window worth of chunks of one clip
+  int clip;
+  int chunk0, n_chunks;
+  int tokens;
+};
+
+struct MicroBatch {
+  std::vector<ChunkDesc> cd;
+  std::vector<int> w2, w3, row_token;
+  std::vector<int2> win;
+  int tokens = 0;
+  int max_win = 0;
+};
+
+int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long mel_ld, const MicroBatch& mb, bf16* out,
+                   cudaStream_t stream) {
+  const qasr_config_t& c = h->cfg;
+  const int nc = static_cast<int>(mb.cd.size());
+  const int ntok = mb.tokens;
+  const int d = c.d_model;
+  if (nc == 0 || ntok == 0) return 0;
+
+  // ---- tables -> device (one pinned block, one copy)
+  const size_t o_cd = 0;
+  const size_t o_w2 = align_up(o_cd + nc * sizeof(ChunkDesc), 16);
+  const size_t o_w3 = align_up(o_w2 + nc * sizeof(int), 16);
+  const size_t o_rt = align_up(o_w3 + nc * sizeof(int), 16);
+  const size_t o_win = align_up(o_rt + static_cast<size_t>(nc) * kTokPerChunk * sizeof(int), 16);
+  const size_t total = align_up(o_win + mb.win.size() * sizeof(int2), 16);
+  Staging* st = nullptr;
+  if (staging_acquire(h, total, &st) != 0) return 2;
+  std::memcpy(st->host + o_cd, mb.cd.data(), nc * sizeof(ChunkDesc));
+  std::memcpy(st->host + o_w2, mb.w2.data(), nc * sizeof(int));
+  std::memcpy(st->host + o_w3, mb.w3.data(), nc * sizeof(int));
+  std::memcpy(st->host + o_rt, mb.row_token.data(), static_cast<size_t>(nc) * kTokPerChunk * sizeof(int));
+  std::memcpy(st->host + o_win, mb.win.data(), mb.win.size() * sizeof(int2));
+  QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
+  const ChunkDesc* d_cd = reinterpret_cast<const ChunkDesc*>(st->dev + o_cd);
+  const int* d_w2 = reinterpret_cast<const int*>(st->dev + o_w2);
+  const int* d_w3 = reinterpret_cast<const int*>(st->dev + o_w3);
+  const int* d_rt = reinterpret_cast<const int*>(st->dev + o_rt);
+  const int2* d_win = reinterpret_cast<const int2*>(st->dev + o_win);
+
+  // ---- conv stem
+  double px1 = 0, px2 = 0, px3 = 0;  // valid output pixels of conv1 / conv2 / conv3 (algorithmic FLOP accounting)
+  for (int i = 0; i < nc; ++i) {
+    px1 += 64.0 * mb.cd[i].w1;
+    px2 += 32.0 * mb.w2[i];
+    px3 += 16.0 * mb.w3[i];
+  }
+  double att_flops = 0;
+  for (const int2& w : mb.win) att_flops += 4.0 * w.y * w.y * d;
+  QASR_LAUNCH(h, "conv1", px1 * kConvC * 18.0, stream,
+              launch_conv1(mel, mel_is_bf16, mel_ld, d_cd, nc, h->conv1_w, h->conv1_b, kConvC, h->act1, stream));
+  {
+    ConvArgs a{};
+    a.tm_a = &h->tm_act1; a.tm_b = &h->tm_conv2_w;
+    a.a = h->act1; a.g_in = static_cast<long long>(h->max_chunks) * ACT1_PITCH; a.h_in = ACT1_H;
+    a.b = h->conv2_w; a.n_chunks = nc; a.hc = 32; a.gt = 4; a.slots = 26; a.max_w = 25; a.out_pitch = 26; a.out_off = 1;
+    a.width = d_w2; a.bias = h->conv2_b; a.out = h->act2; a.c = kConvC;
+    QASR_LAUNCH(h, "conv2_gemm", px2 * kConvC * 2.0 * 9 * kConvC, stream, gemm_conv(a, h->simt, h->num_sms, stream));
+  }
+  {
+    ConvArgs a{};
+    a.tm_a = &h->tm_act2; a.tm_b = &h->tm_conv3_w;
+    a.a = h->act2; a.g_in = static_cast<long long>(h->max_chunks) * 26; a.h_in = 32;
+    a.b = h->conv3_w; a.n_chunks = nc; a.hc = 16; a.gt = 8; a.slots = 13; a.max_w = 13; a.out_pitch = 13; a.out_off = 0;
+    a.width = d_w3; a.bias = h->conv3_b; a.out = h->act3; a.c = kConvC;
+    QASR_LAUNCH(h, "conv3_gemm", px3 * kConvC * 2.0 * 9 * kConvC, stream, gemm_conv(a, h->simt, h->num_sms, stream));
+  }
+  {
+    ConvOutArgs a{};
+    a.tm_a = &h->tm_act3; a.tm_b = &h->conv_out.tm; a.bn = h->conv_out.bn;
+    a.a = h->act3; a.b = h->conv_out.w; a.m = nc * kTokPerChunk; a.d = d; a.k = 16 * kConvC;
+    a.pe = h->pe; a.row_token = d_rt; a.tok_per_chunk = kTokPerChunk; a.out = h->x;
+    QASR_LAUNCH(h, "conv_out_gemm", 2.0 * ntok * 16 * kConvC * d, stream, gemm_conv_out(a, h->simt, h->num_sms, stream));
+  }
+  if (h->keep_debug && h->embed_dbg != nullptr)
+    QASR_CUDA_CHECK(cudaMemcpyAsync(h->embed_dbg, h->x, static_cast<size_t>(ntok) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
+
+  // ---- transformer layers
+  auto linear = [&](const CUtensorMap* tm_a, const bf16* a_raw, const LinearW& w, int epi, bf16* o, long long ldo,
+                    const bf16* residual) -> cudaError_t {
+    LinearArgs la{};
+    la.tm_a = tm_a; la.tm_b = &w.tm; la.bn = w.bn; la.a = a_raw; la.lda = w.k; la.b = w.w; la.ldb = w.k;
+    la.m = ntok; la.n = w.n; la.k = w.k; la.epi = epi; la.out = o; la.ldo = ldo; la.bias = w.b; la.residual = residual;
+    return gemm_linear(la, h->simt, h->num_sms, stream);
+  };
+  const int n_win = static_cast<int>(mb.win.size());
+  for (const LayerW& L : h->layers) {
+    const double tk = 2.0 * ntok;
+    QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, L.ln1_g, L.ln1_b, h->hbuf, ntok, d, 1e-5f, stream));
+    QASR_LAUNCH(h, "qkv_gemm", tk * 3 * d * d, stream, linear(&h->tm_h, h->hbuf, L.qkv, LIN_PLAIN, h->qkv, 3LL * d, nullptr));
+    QASR_LAUNCH(h, "window_attention", att_flops, stream,
+                launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, stream));
+    QASR_LAUNCH(h, "out_proj_gemm", tk * d * d, stream, linear(&h->tm_att, h->att, L.out, LIN_RESIDUAL, h->x, d, h->x));
+    QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, L.ln2_g, L.ln2_b, h->hbuf, ntok, d, 1e-5f, stream));
+    QASR_LAUNCH(h, "fc1_gemm", tk * d * c.encoder_ffn_dim, stream, linear(&h->tm_h, h->hbuf, L.fc1, LIN_GELU, h->ffn, c.encoder_ffn_dim, nullptr));
+    QASR_LAUNCH(h, "fc2_gemm", tk * d * c.encoder_ffn_dim, stream, linear(&h->tm_ffn, h->ffn, L.fc2, LIN_RESIDUAL, h->x, d, h->x));
+  }
+  // ---- output head
+  QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, h->lnp_g, h->lnp_b, h->hbuf, ntok, d, 1e-5f, stream));
+  QASR_LAUNCH(h, "proj1_gemm", 2.0 * ntok * d * d, stream, linear(&h->tm_h, h->hbuf, h->proj1, LIN_GELU, h->att, d, nullptr));
+  QASR_LAUNCH(h, "proj2_gemm", 2.0 * ntok * d * c.output_dim, stream, linear(&h->tm_att, h->att, h->proj2, LIN_PLAIN, out, c.output_dim, nullptr));
+
+  QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
+  st->in_flight = true;
+  h->last_chunks = nc;
+  h->last_tokens = ntok;
+  return 0;
+}
+
+}  // namespace
+
+// ==============================================================================================
+// C ABI
+// ==============================================================================================
+extern "C" {
+
+int qasr_abi_version(void) { return QASR_ABI_VERSION; }
+
+const char* qasr_last_error(void) { return g_last_error.c_str(); }
+
+int64_t qasr_token_len(int64_t feature_len) {
+  if (feature_len <= 0) return 0;
+  const int r = static_cast<int>(feature_len % 100);
+  return conv_len3(r) + (feature_len / 100) * kTokPerChunk;
+}
+
+int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
+  QASR_REQUIRE(cfg != nullptr && out != nullptr, "qasr_create: null argument");
+  QASR_REQUIRE(cfg->num_mel_bins == 128, "num_mel_bins must be 128");
+  QASR_REQUIRE(cfg->n_window == 50, "n_window must be 50 (100-frame conv chunks)");
+  QASR_REQUIRE(cfg->downsample_hidden_size == kConvC, "downsample_hidden_size must be 480");
+  QASR_REQUIRE(cfg->encoder_attention_heads > 0 && cfg->d_model == cfg->encoder_attention_heads * 64, "head_dim must be 64");
+  QASR_REQUIRE(cfg->n_window_infer >= 100 && cfg->n_window_infer % 100 == 0, "n_window_infer must be a positive multiple of 100");
+  QASR_REQUIRE(cfg->encoder_layers >= 0 && cfg->encoder_ffn_dim > 0 && cfg->output_dim > 0, "bad layer dims");
+  QASR_REQUIRE(cfg->flags == 0, "flags must be 0");
+  int n_dev = 0;
+  QASR_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+  QASR_REQUIRE(device >= 0 && device < n_dev, "no such CUDA device");
+  cudaDeviceProp prop;
+  QASR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  QASR_REQUIRE(prop.major == 10, "qasr_b200 needs an sm_100 (B200) device; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  DeviceGuard guard(device);
+  if (tmap_api_init() != 0) return 2;
+
+  qasr_handle_s* h = new qasr_handle_s();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->chunks_per_window = cfg->n_window_infer / 100;
+  h->max_chunks = cfg->max_chunks > 0 ? cfg->max_chunks : 1024;
+  h->max_tokens = cfg->max_tokens > 0 ? cfg->max_tokens : h->max_chunks * kTokPerChunk;
+  h->max_chunks = std::max(h->max_chunks, h->chunks_per_window);
+  h->max_tokens = std::max(h->max_tokens, h->chunks_per_window * kTokPerChunk);
+  const char* e = std::getenv("QASR_DEBUG_SIMT");
+  h->simt = e != nullptr && e[0] == '1';
+  e = std::getenv("QASR_DEBUG_KEEP");
+  h->keep_debug = e != nullptr && e[0] == '1';
+
+  mel::Tables* host_tables = new mel::Tables();
+  build_mel_tables(host_tables);
+  int rc = dev_alloc(h, reinterpret_cast<void**>(&h->mel_tables), sizeof(mel::Tables));
+  if (rc == 0 && cudaMemcpy(h->mel_tables, host_tables, sizeof(mel::Tables), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_last_error("uploading the mel tables failed");
+    rc = 2;
+  }
+  delete host_tables;
+  if (rc != 0) {
+    qasr_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int qasr_set_weight(qasr_handle_t h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim) {
+  QASR_REQUIRE(h != nullptr && name != nullptr && data != nullptr && shape != nullptr && ndim >= 1 && ndim <= 4, "qasr_set_weight: bad argument");
+  QASR_REQUIRE(!h->finalized, "qasr_set_weight after qasr_finalize");
+  DeviceGuard guard(h->device);
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  QASR_REQUIRE(n > 0, "qasr_set_weight: empty tensor");
+  t.data.resize(n);
+  if (dtype == QASR_F32) {
+    QASR_CUDA_CHECK(cudaMemcpy(t.data.data(), data, n * sizeof(float), cudaMemcpyDefault));
+  } else if (dtype == QASR_BF16 || dtype == QASR_F16) {
+    std::vector<uint16_t> raw(n);
+    QASR_CUDA_CHECK(cudaMemcpy(raw.data(), data, n * sizeof(uint16_t), cudaMemcpyDefault));
+    for (int64_t i = 0; i < n; ++i) {
+      if (dtype == QASR_BF16) {
+        const uint32_t u = static_cast<uint32_t>(raw[i]) << 16;
+        std::memcpy(&t.data[i], &u, 4);
+      } else {
+        __half hv;
+        std::memcpy(&hv, &raw[i], 2);
+        t.data[i] = __half2float(hv);
+      }
+    }
+  } else {
+    set_last_error("qasr_set_weight: unknown dtype");
+    return 1;
+  }
+  h->staged[name] = std::move(t);
+  return 0;
+}
+
+int qasr_finalize(qasr_handle_t h) {
+  QASR_REQUIRE(h != nullptr, "qasr_finalize: null handle");
+  QASR_REQUIRE(!h->finalized, "qasr_finalize called twice");
+  DeviceGuard guard(h->device);
+  const qasr_config_t& c = h->cfg;
+  const int d = c.d_model, ffn = c.encoder_ffn_dim;
+  int rc;
+
+  // ---- conv stem
+  {
+    const HostTensor *w = nullptr, *b = nullptr;
+    if ((rc = need_weight(h, "conv2d1.weight", {kConvC, 1, 3, 3}, &w)) != 0) return rc;
+    if ((rc = need_weight(h, "conv2d1.bias", {kConvC}, &b)) != 0) return rc;
+    if ((rc = upload_f32(h, w->data.data(), kConvC * 9, &h->conv1_w)) != 0) return rc;
+    if ((rc = upload_f32(h, b->data.data(), kConvC, &h->conv1_b)) != 0) return rc;
+  }
+  if ((rc = load_conv(h, "conv2d2", &h->conv2_w, &h->conv2_b, &h->tm_conv2_w)) != 0) return rc;
+  if ((rc = load_conv(h, "conv2d3", &h->conv3_w, &h->conv3_b, &h->tm_conv3_w)) != 0) return rc;
+  {
+    // conv_out.weight [d, 7680] with K index c*16+f -> f*480+c (modeling_qwen3_omni_moe.py:735-736)
+    const HostTensor* w = nullptr;
+    if ((rc = need_weight(h, "conv_out.weight", {d, 16 * kConvC}, &w)) != 0) return rc;
+    std::vector<float> perm(static_cast<size_t>(d) * 16 * kConvC);
+    for (int n = 0; n < d; ++n)
+      for (int ch = 0; ch < kConvC; ++ch)
+        for (int f = 0; f < 16; ++f)
+          perm[static_cast<size_t>(n) * 7680 + f * kConvC + ch] = w->data[static_cast<size_t>(n) * 7680 + ch * 16 + f];
+    if ((rc = make_linear(h, perm.data(), nullptr, d, 16 * kConvC, &h->conv_out)) != 0) return rc;
+  }
+  {
+    // sinusoid table rows 0..12 (positions restart in every chunk), values rounded to bf16
+    std::vector<float> pe(static_cast<size_t>(kTokPerChunk) * d);
+    const HostTensor* given = find_weight(h, "positional_embedding");
+    if (given != nullptr) {
+      QASR_REQUIRE(given->shape.size() == 2 && given->shape[1] == d && given->shape[0] >= kTokPerChunk, "positional_embedding must be [>=13, d_model]");
+      std::memcpy(pe.data(), given->data.data(), pe.size() * sizeof(float));
+    } else {
+      const int half = d / 2;
+      const float inc = static_cast<float>(std::log(10000.0) / (half - 1));
+      for (int p = 0; p < kTokPerChunk; ++p)
+        for (int j = 0; j < half; ++j) {
+          const float inv = std::exp(-inc * static_cast<float>(j));
+          const float st = static_cast<float>(p) * inv;
+          pe[static_cast<size_t>(p) * d + j] = std::sin(st);
+          pe[static_cast<size_t>(p) * d + half + j] = std::cos(st);
+        }
+    }
+    for (float& v : pe) v = __bfloat162float(__float2bfloat16_rn(v));
+    if ((rc = upload_f32(h, pe.data(), pe.size(), &h->pe)) != 0) return rc;
+  }
+
+  // ---- transformer layers
+  h->layers.resize(c.encoder_layers);
+  for (int i = 0; i < c.encoder_layers; ++i) {
+    const std::string p = "layers." + std::to_string(i) + ".";
+    LayerW& L = h->layers[i];
+    {
+      const HostTensor *wq, *wk, *wv, *bq, *bk, *bv;
+      if ((rc = need_weight(h, p + "self_attn.q_proj.weight", {d, d}, &wq)) != 0) return rc;
+      if ((rc = need_weight(h, p + "self_attn.k_proj.weight", {d, d}, &wk)) != 0) return rc;
+      if ((rc = need_weight(h, p + "self_attn.v_proj.weight", {d, d}, &wv)) != 0) return rc;
+      if ((rc = need_weight(h, p + "self_attn.q_proj.bias", {d}, &bq)) != 0) return rc;
+      if ((rc = need_weight(h, p + "self_attn.k_proj.bias", {d}, &bk)) != 0) return rc;
+      if ((rc = need_weight(h, p + "self_attn.v_proj.bias", {d}, &bv)) != 0) return rc;
+      std::vector<float> w(static_cast<size_t>(3) * d * d), b(static_cast<size_t>(3) * d);
+      std::memcpy(w.data(), wq->data.data(), sizeof(float) * d * d);
+      std::memcpy(w.data() + static_cast<size_t>(d) * d, wk->data.data(), sizeof(float) * d * d);
+      std::memcpy(w.data() + static_cast<size_t>(2) * d * d, wv->data.data(), sizeof(float) * d * d);
+      std::memcpy(b.data(), bq->data.data(), sizeof(float) * d);
+      std::memcpy(b.data() + d, bk->data.data(), sizeof(float) * d);
+      std::memcpy(b.data() + 2 * d, bv->data.data(), sizeof(float) * d);
+      if ((rc = make_linear(h, w.data(), b.data(), 3 * d, d, &L.qkv)) != 0) return rc;
+    }
+    if ((rc = load_linear(h, p + "self_attn.out_proj", d, d, true, &L.out)) != 0) return rc;
+    if ((rc = load_linear(h, p + "fc1", ffn, d, true, &L.fc1)) != 0) return rc;
+    if ((rc = load_linear(h, p + "fc2", d, ffn, true, &L.fc2)) != 0) return rc;
+    if ((rc = load_vec(h, p + "self_attn_layer_norm.weight", d, &L.ln1_g)) != 0) return rc;
+    if ((rc = load_vec(h, p + "self_attn_layer_norm.bias", d, &L.ln1_b)) != 0) return rc;
+    if ((rc = load_vec(h, p + "final_layer_norm.weight", d, &L.ln2_g)) != 0) return rc;
+    if ((rc = load_vec(h, p + "final_layer_norm.bias", d, &L.ln2_b)) != 0) return rc;
+  }
+  if ((rc = load_vec(h, "ln_post.weight", d, &h->lnp_g)) != 0) return rc;
+  if ((rc = load_vec(h, "ln_post.bias", d, &h->lnp_b)) != 0) return rc;
+  if ((rc = load_linear(h, "proj1", d, d, true, &h->proj1)) != 0) return rc;
+  if ((rc = load_linear(h, "proj2", c.output_dim, d, true, &h->proj2)) != 0) return rc;
+  h->staged.clear();
+
+  // ---- workspace
+  const size_t mc = h->max_chunks;
+  const size_t mt = align_up(h->max_tokens, 128);
+  const size_t act1_elems = mc * ACT1_PITCH * ACT1_H * kConvC;
+  const size_t act2_elems = mc * 26 * 32 * kConvC;
+  const size_t act3_elems = mc * kTokPerChunk * 16 * kConvC;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->act1), act1_elems * sizeof(bf16))) != 0) return rc;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->act2), act2_elems * sizeof(bf16))) != 0) return rc;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->act3), act3_elems * sizeof(bf16))) != 0) return rc;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->x), mt * d * sizeof(bf16))) != 0) return rc;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->hbuf), mt * d * sizeof(bf16))) != 0) return rc;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->qkv), mt * 3 * d * sizeof(bf16))) != 0) return rc;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->att), mt * d * sizeof(bf16))) != 0) return rc;
+  if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->ffn), mt * ffn * sizeof(bf16))) != 0) return rc;
+  if (h->keep_debug && (rc = dev_alloc(h, reinterpret_cast<void**>(&h->embed_dbg), mt * d * sizeof(bf16))) != 0) return rc;
+  // act2's column 0 of every chunk is conv3's left zero padding and is never written afterwards
+  QASR_CUDA_CHECK(cudaMemset(h->act2, 0, act2_elems * sizeof(bf16)));
+  QASR_CUDA_CHECK(cudaMemset(h->act3, 0, act3_elems * sizeof(bf16)));
+  QASR_CUDA_CHECK(cudaMemset(h->x, 0, mt * d * sizeof(bf16)));
+
+  if ((rc = make_tmap_conv(&h->tm_act1, h->act1, static_cast<long long>(mc) * ACT1_PITCH, ACT1_H, kConvC, 32, 4)) != 0) return rc;
+  if ((rc = make_tmap_conv(&h->tm_act2, h->act2, static_cast<long long>(mc) * 26, 32, kConvC, 16, 8)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor(&h->tm_act3, h->act3, static_cast<long long>(mc) * kTokPerChunk, 16 * kConvC, 16 * kConvC, 128)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor(&h->tm_h, h->hbuf, mt, d, d, 128)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor(&h->tm_att, h->att, mt, d, d, 128)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor(&h->tm_ffn, h->ffn, mt, ffn, ffn, 128)) != 0) return rc;
+  QASR_CUDA_CHECK(cudaDeviceSynchronize());
+  h->finalized = true;
+  return 0;
+}
+
+size_t qasr_workspace_bytes(qasr_handle_t h) { return h == nullptr ? 0 : h->device_bytes; }
+
+int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, float* mel_out_dev, int64_t mel_ld,
+                int64_t* feature_lens_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_logmel: bad argument");
+  if (n_clips == 0) return 0;
+  QASR_REQUIRE(pcm_dev != nullptr && mel_out_dev != nullptr, "qasr_logmel: null buffer");
+  QASR_REQUIRE(n_clips <= 65535, "qasr_logmel: at most 65535 clips per call");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+  long long cols = 0;
+  size_t n_slabs = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
+    QASR_REQUIRE(n > mel::N_FFT / 2, "qasr_logmel: every clip needs more than 200 samples (reflect padding), clip " + std::to_string(i) +
+                                        " has " + std::to_string(n));
+    QASR_REQUIRE(n < (1LL << 31), "qasr_logmel: clip too long");
+    const int64_t t = n / mel::HOP;
+    if (feature_lens_out != nullptr) feature_lens_out[i] = t;
+    cols += t;
+    n_slabs += static_cast<size_t>((t + mel::FB - 1) / mel::FB);
+  }
+  QASR_REQUIRE(mel_ld >= cols, "qasr_logmel: mel_ld smaller than the total frame count");
+  if (cols == 0) return 0;
+
+  const size_t o_slab = 0;
+  const size_t o_cols = align_up(n_slabs * sizeof(MelSlab), 16);
+  const size_t total = o_cols + (static_cast<size_t>(n_clips) + 1) * sizeof(long long);
+  Staging* st = nullptr;
+  if (staging_acquire(h, total, &st) != 0) return 2;
+  MelSlab* slabs = reinterpret_cast<MelSlab*>(st->host + o_slab);
+  long long* ccols = reinterpret_cast<long long*>(st->host + o_cols);
+  size_t si = 0;
+  long long col = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
+    const int t = static_cast<int>(n / mel::HOP);
+    ccols[i] = col;
+    for (int f0 = 0; f0 < t; f0 += mel::FB) {
+      MelSlab& s = slabs[si++];
+      s.clip = i;
+      s.frame0 = f0;
+      s.n_frames = std::min(mel::FB, t - f0);
+      s.n_samples = static_cast<int>(n);
+      s.pcm_off = clip_offsets[i];
+      s.col0 = col;
+    }
+    col += t;
+  }
+  ccols[n_clips] = col;
+  QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
+  if (grow(h, &h->clipmax_buf, static_cast<size_t>(n_clips) * sizeof(unsigned int)) != 0) return 2;
+  unsigned int* cmax = static_cast<unsigned int*>(h->clipmax_buf.p);
+  QASR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, static_cast<size_t>(n_clips) * sizeof(unsigned int), stream));
+  const double mel_bytes = 4.0 * static_cast<double>(clip_offsets[n_clips] - clip_offsets[0]) + 4.0 * mel::N_MELS * static_cast<double>(cols);
+  QASR_LAUNCH(h, "logmel", mel_bytes, stream,
+              launch_logmel(pcm_dev, reinterpret_cast<const MelSlab*>(st->dev + o_slab), static_cast<int>(n_slabs), h->mel_tables,
+                            mel_out_dev, mel_ld, cmax, stream));
+  QASR_LAUNCH(h, "logmel_finish", 0, stream,
+              launch_logmel_finish(mel_out_dev, mel_ld, reinterpret_cast<const long long*>(st->dev + o_cols), n_clips, cmax, stream));
+  QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
+  st->in_flight = true;
+  h->last_mel_cols = cols;
+  h->last_mel_ld = mel_ld;
+  return 0;
+}
+
+int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
+                void* out_dev, int64_t* token_lens_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && feature_lens != nullptr && n_clips >= 0, "qasr_encode: bad argument");
+  QASR_REQUIRE(h->finalized, "qasr_encode before qasr_finalize");
+  QASR_REQUIRE(mel_dtype == QASR_F32 || mel_dtype == QASR_BF16, "qasr_encode: mel dtype must be f32 or bf16");
+  if (n_clips == 0) return 0;
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int cpw = h->chunks_per_window;
+
+  // ---- plan: window-sized units of chunks, clip-major (the order of the output rows)
+  std::vector<Unit> units;
+  std::vector<long long> clip_col0(n_clips);
+  long long col = 0, total_tokens = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t t = feature_lens[i];
+    QASR_REQUIRE(t >= 0 && t < (1LL << 30), "qasr_encode: bad feature length");
+    clip_col0[i] = col;
+    col += t;
+    const int64_t ntok = qasr_token_len(t);
+    if (token_lens_out != nullptr) token_lens_out[i] = ntok;
+    total_tokens += ntok;
+    const int n_chunks = static_cast<int>((t + 99) / 100);
+    for (int c0 = 0; c0 < n_chunks; c0 += cpw) {
+      Unit u;
+      u.clip = i;
+      u.chunk0 = c0;
+      u.n_chunks = std::min(cpw, n_chunks - c0);
+      int tok = 0;
+      for (int j = c0; j < c0 + u.n_chunks; ++j) tok += conv_len3(static_cast<int>(std::min<int64_t>(100, t - 100LL * j)));
+      u.tokens = tok;
+      units.push_back(u);
+    }
+  }
+  QASR_REQUIRE(mel_ld >= col, "qasr_encode: mel_ld smaller than the total frame count");
+  if (total_tokens == 0) return 0;
+  QASR_REQUIRE(mel_dev != nullptr && out_dev != nullptr, "qasr_encode: null buffer");
+
+  size_t ui = 0;
+  long long tok_off = 0;
+  MicroBatch mb;
+  while (ui < units.size()) {
+    mb.cd.clear(); mb.w2.clear(); mb.w3.clear(); mb.row_token.clear(); mb.win.clear();
+    mb.tokens = 0;
+    mb.max_win = 0;
+    int chunks = 0;
+    while (ui < units.size() && chunks + units[ui].n_chunks <= h->max_chunks && mb.tokens + units[ui].tokens <= h->max_tokens) {
+      const Unit& u = units[ui];
+      const int64_t t = feature_lens[u.clip];
+      const bool lone_short = t < 100;  // padded only to its own length
+      mb.win.push_back(make_int2(mb.tokens, u.tokens));
+      mb.max_win = std::max(mb.max_win, u.tokens);
+      int tok = mb.tokens;
+      for (int j = u.chunk0; j < u.chunk0 + u.n_chunks; ++j) {
+        const int valid = static_cast<int>(std::min<int64_t>(100, t - 100LL * j));
+        const int padded = lone_short ? valid : 100;
+        ChunkDesc cd;
+        cd.mel_col0 = clip_col0[u.clip] + 100LL * j;
+        cd.valid = valid;
+        cd.w1 = conv_len(padded);
+        mb.cd.push_back(cd);
+        mb.w2.push_back(conv_len(cd.w1));
+        mb.w3.push_back(conv_len(conv_len(cd.w1)));
+        const int nt = conv_len3(valid);
+        for (int k = 0; k < kTokPerChunk; ++k) mb.row_token.push_back(k < nt ? tok++ : -1);
+      }
+      mb.tokens += u.tokens;
+      chunks += u.n_chunks;
+      ++ui;
+    }
+    QASR_REQUIRE(chunks > 0, "qasr_encode: a single attention window exceeds the micro-batch capacity");
+    const int rc = run_microbatch(h, mel_dev, mel_dtype == QASR_BF16, mel_ld, mb,
+                                  static_cast<bf16*>(out_dev) + tok_off * h->cfg.output_dim, stream);
+    if (rc != 0) return rc;
+    tok_off += mb.tokens;
+  }
+  h->last_mel_cols = col;
+  h->last_mel_ld = mel_ld;
+  return 0;
+}
+
+int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, void* out_dev,
+                    int64_t* token_lens_out, void* stream) {
+  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_encode_pcm: bad argument");
+  QASR_REQUIRE(h->finalized, "qasr_encode_pcm before qasr_finalize");
+  if (n_clips == 0) return 0;
+  DeviceGuard guard(h->device);
+  std::vector<int64_t> flens(n_clips);
+  long long cols = 0;
+  for (int i = 0; i < n_clips; ++i) cols += (clip_offsets[i + 1] - clip_offsets[i]) / mel::HOP;
+  const long long ld = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(cols, 1)), 8));
+  if (grow(h, &h->mel_buf, static_cast<size_t>(ld) * mel::N_MELS * sizeof(float)) != 0) return 2;
+  float* mel = static_cast<float*>(h->mel_buf.p);
+  int rc = qasr_logmel(h, pcm_dev, clip_offsets, n_clips, mel, ld, flens.data(), stream);
+  if (rc != 0) return rc;
+  return qasr_encode(h, mel, QASR_F32, ld, flens.data(), n_clips, out_dev, token_lens_out, stream);
+}
+
+int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_encode_pcm_host: bad argument");
+  QASR_REQUIRE(h->finalized, "qasr_encode_pcm_host before qasr_finalize");
+  if (n_clips == 0) return 0;
+  QASR_REQUIRE(pcm_host != nullptr && out_host != nullptr, "qasr_encode_pcm_host: null buffer");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int64_t base = clip_offsets[0];
+  const int64_t n_samples = clip_offsets[n_clips] - base;
+  long long tokens = 0;
+  std::vector<int64_t> offs(n_clips + 1);
+  for (int i = 0; i <= n_clips; ++i) offs[i] = clip_offsets[i] - base;
+  for (int i = 0; i < n_clips; ++i) tokens += qasr_token_len((offs[i + 1] - offs[i]) / mel::HOP);
+  QASR_REQUIRE(tokens <= out_capacity_tokens, "qasr_encode_pcm_host: output buffer too small for " + std::to_string(tokens) + " tokens");
+  if (grow(h, &h->pcm_buf, static_cast<size_t>(n_samples) * sizeof(float)) != 0) return 2;
+  const size_t out_bytes = static_cast<size_t>(tokens) * h->cfg.output_dim * sizeof(bf16);
+  if (grow(h, &h->out_buf, out_bytes) != 0) return 2;
+  QASR_CUDA_CHECK(cudaMemcpyAsync(h->pcm_buf.p, pcm_host + base, static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, stream));
+  const int rc = qasr_encode_pcm(h, static_cast<const float*>(h->pcm_buf.p), offs.data(), n_clips, h->out_buf.p, token_lens_out, stream);
+  if (rc != 0) return rc;
+  if (out_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(out_host, h->out_buf.p, out_bytes, cudaMemcpyDeviceToHost, stream));
+  QASR_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
+                     int64_t* feature_lens_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_logmel_host: bad argument");
+  if (n_clips == 0) return 0;
+  QASR_REQUIRE(pcm_host != nullptr && mel_out_host != nullptr, "qasr_logmel_host: null buffer");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int64_t base = clip_offsets[0];
+  const int64_t n_samples = clip_offsets[n_clips] - base;
+  std::vector<int64_t> offs(n_clips + 1);
+  long long cols = 0;
+  for (int i = 0; i <= n_clips; ++i) offs[i] = clip_offsets[i] - base;
+  for (int i = 0; i < n_clips; ++i) cols += (offs[i + 1] - offs[i]) / mel::HOP;
+  if (cols == 0) return 0;
+  if (grow(h, &h->pcm_buf, static_cast<size_t>(n_samples) * sizeof(float)) != 0) return 2;
+  if (grow(h, &h->mel_buf, static_cast<size_t>(cols) * mel::N_MELS * sizeof(float)) != 0) return 2;
+  QASR_CUDA_CHECK(cudaMemcpyAsync(h->pcm_buf.p, pcm_host + base, static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, stream));
+  const int rc = qasr_logmel(h, static_cast<const float*>(h->pcm_buf.p), offs.data(), n_clips, static_cast<float*>(h->mel_buf.p), cols,
+                             feature_lens_out, stream);
+  if (rc != 0) return rc;
+  QASR_CUDA_CHECK(cudaMemcpyAsync(mel_out_host, h->mel_buf.p, static_cast<size_t>(cols) * mel::N_MELS * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  QASR_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+void qasr_destroy(qasr_handle_t h) {
+  if (h == nullptr) return;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  for (Staging& s : h->staging) {
+    if (s.host != nullptr) cudaFreeHost(s.host);
+    if (s.dev != nullptr) cudaFree(s.dev);
+    if (s.ev != nullptr) cudaEventDestroy(s.ev);
+  }
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+  for (GrowBuf* b : {&h->mel_buf, &h->pcm_buf, &h->out_buf, &h->clipmax_buf})
+    if (b->p != nullptr) cudaFree(b->p);
+  delete h;
+}
+
+// ---- launch accounting / per-launch timing ------------------------------------------------------
+uint64_t qasr_launch_count(qasr_handle_t h) { return h == nullptr ? 0 : h->launches; }
+
+int qasr_profile_enable(qasr_handle_t h, int on) {
+  QASR_REQUIRE(h != nullptr, "qasr_profile_enable: null handle");
+  DeviceGuard guard(h->device);
+  QASR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (auto& r : h->prof) {
+    h->event_pool.push_back(r.e0);
+    h->event_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  h->profiling = on != 0;
+  return 0;
+}
+
+int qasr_profile_read(qasr_handle_t h, char* names, size_t names_cap, double* ms, double* work, int32_t* counts, int max_entries,
+                      int* n_entries) {
+  QASR_REQUIRE(h != nullptr && names != nullptr && ms != nullptr && work != nullptr && counts != nullptr && n_entries != nullptr,
+               "qasr_profile_read: bad argument");
+  DeviceGuard guard(h->device);
+  QASR_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<std::string> order;
+  std::map<std::string, int> index;
+  std::vector<double> t_ms, t_work;
+  std::vector<int> t_cnt;
+  for (auto& r : h->prof) {
+    float e = 0.f;
+    QASR_CUDA_CHECK(cudaEventElapsedTime(&e, r.e0, r.e1));
+    auto it = index.find(r.name);
+    int k;
+    if (it == index.end()) {
+      k = static_cast<int>(order.size());
+      index[r.name] = k;
+      order.push_back(r.name);
+      t_ms.push_back(0); t_work.push_back(0); t_cnt.push_back(0);
+    } else {
+      k = it->second;
+    }
+    t_ms[k] += e; t_work[k] += r.work; t_cnt[k] += 1;
+  }
+  QASR_REQUIRE(static_cast<int>(order.size()) <= max_entries, "qasr_profile_read: too many entries");
+  std::string joined;
+  for (size_t i = 0; i < order.size(); ++i) {
+    joined += order[i];
+    joined += '\n';
+    ms[i] = t_ms[i]; work[i] = t_work[i]; counts[i] = t_cnt[i];
+  }
+  QASR_REQUIRE(joined.size() + 1 <= names_cap, "qasr_profile_read: names buffer too small");
+  std::memcpy(names, joined.c_str(), joined.size() + 1);
+  *n_entries = static_cast<int>(order.size());
+  return 0;
+}
+
+// ---- test / bring-up hooks --------------------------------------------------------------------
+int qasr_debug_read(qasr_handle_t h, const char* name, void* dst_host, size_t capacity, size_t* nbytes) {
+  QASR_REQUIRE(h != nullptr && name != nullptr && dst_host != nullptr && nbytes != nullptr, "qasr_debug_read: bad argument");
+  DeviceGuard guard(h->device);
+  QASR_CUDA_CHECK(cudaDeviceSynchronize());
+  const std::string n(name);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  const size_t nc = h->last_chunks;
+  if (n == "act1") { src = h->act1; bytes = nc * ACT1_PITCH * ACT1_H * kConvC * sizeof(bf16); }
+  else if (n == "act2") { src = h->act2; bytes = nc * 26 * 32 * kConvC * sizeof(bf16); }
+  else if (n == "act3") { src = h->act3; bytes = nc * kTokPerChunk * 16 * kConvC * sizeof(bf16); }
+  else if (n == "embed") { src = h->embed_dbg; bytes = static_cast<size_t>(h->last_tokens) * h->cfg.d_model * sizeof(bf16); }
+  else if (n == "mel") { src = h->mel_buf.p; bytes = static_cast<size_t>(h->last_mel_ld) * mel::N_MELS * sizeof(float); }
+  else { set_last_error("qasr_debug_read: unknown name " + n); return 1; }
+  QASR_REQUIRE(src != nullptr, "qasr_debug_read: " + n + " is not available (set QASR_DEBUG_KEEP=1 before qasr_create for embed)");
+  QASR_REQUIRE(bytes <= capacity, "qasr_debug_read: destination too small, need " + std::to_string(bytes));
+  QASR_CUDA_CHECK(cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost));
+  *nbytes = bytes;
+  return 0;
+}
+
+int qasr_debug_gemm(const void* a, const void* b, const float* bias, const void* residual, void* d, int m, int n, int k, int act,
+                    int impl, void* stream_v) {
+  QASR_REQUIRE(a != nullptr && b != nullptr && d != nullptr && m > 0 && n > 0 && k > 0, "qasr_debug_gemm: bad argument");
+  QASR_REQUIRE(k % 64 == 0, "qasr_debug_gemm: k must be a multiple of 64");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int bn = pick_bn(n);
+  QASR_REQUIRE(impl == 1 || bn != 0, "qasr_debug_gemm: n must be a multiple of 64");
+  QASR_REQUIRE(n % 16 == 0, "qasr_debug_gemm: n must be a multiple of 16");
+  CUtensorMap tm_a, tm_b;
+  if (impl == 0) {
+    int rc;
+    if ((rc = make_tmap_rowmajor(&tm_a, a, m, k, k, 128)) != 0) return rc;
+    if ((rc = make_tmap_rowmajor(&tm_b, b, n, k, k, bn)) != 0) return rc;
+  }
+  int dev = 0, sms = kNumSMs;
+  QASR_CUDA_CHECK(cudaGetDevice(&dev));
+  QASR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LinearArgs la{};
+  la.tm_a = &tm_a; la.tm_b = &tm_b; la.bn = bn;
+  la.a = static_cast<const bf16*>(a); la.lda = k; la.b = static_cast<const bf16*>(b); la.ldb = k;
+  la.m = m; la.n = n; la.k = k;
+  la.epi = residual != nullptr ? LIN_RESIDUAL : (act == 1 ? LIN_GELU : LIN_PLAIN);
+  la.out = static_cast<bf16*>(d); la.ldo = n; la.bias = bias; la.residual = static_cast<const bf16*>(residual);
+  QASR_CUDA_CHECK(gemm_linear(la, impl == 1, sms, stream));
+  return 0;
+}
+
+int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int d, void* stream) {
+  QASR_CUDA_CHECK(launch_layernorm(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(out), rows, d, 1e-5f,
+                                   static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream_v) {
+  QASR_REQUIRE(qkv != nullptr && out != nullptr && win_start_len_host != nullptr && n_win > 0, "qasr_debug_attention: bad argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  int2* dwin = nullptr;
+  QASR_CUDA_CHECK(cudaMalloc(&dwin, n_win * sizeof(int2)));
+  int max_win = 0;
+  for (int i = 0; i < n_win; ++i) max_win = std::max(max_win, win_start_len_host[2 * i + 1]);
+  cudaError_t e = cudaMemcpyAsync(dwin, win_start_len_host, n_win * sizeof(int2), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = launch_window_attention(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(dwin);
+  if (e != cudaSuccess) {
+    set_last_error(std::string("qasr_debug_attention: ") + cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+}  // extern "C"

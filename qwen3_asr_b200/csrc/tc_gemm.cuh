@@ -30,6 +30,7 @@ constexpr int UMMA_K = 16;
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM columns per accumulator stage (2 stages)
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum AMode : int { A_LINEAR = 0, A_CONV = 1 };
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape, Epi epi) {
   using L = SmemLayout<BN, STAGES>;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
-  static_assert(2 * BN <= kTmemCols, "two accumulator stages must fit TMEM");
+  static_assert(BN <= kAccStride, "an accumulator stage is kAccStride TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -245,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kAccStride);
         for (int kb = 0; kb < shape.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -276,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];

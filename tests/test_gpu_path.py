@@ -1,0 +1,292 @@
+"""Parity of the CUDA hot path (through the C ABI) against the oracle and the committed golden
+vectors: log-mel (<= 1e-4 range-relative), encoder hidden states (<= 2e-2 max relative error)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import range_rel
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 1e-4      # north_star: log-mel within 1e-4 relative (range-relative)
+HID_TOL = 2e-2      # north_star: encoder hidden states within bf16 tolerance, max rel err <= 2e-2
+
+
+def _clip(golden, name):
+    from oracle.signals import noise_clip, speech_like
+
+    if f"pcm_{name}" in golden:
+        return golden[f"pcm_{name}"].astype(np.float32) / 32768.0
+    return {
+        "noise5s": lambda: noise_clip(80000, 0),
+        "speech2s": lambda: speech_like(32000, 7),
+        "odd": lambda: noise_clip(80077, 3),
+        "short": lambda: speech_like(7200, 11),
+        "tone": lambda: (0.5 * np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000)).astype(np.float32),
+        "zeros": lambda: np.zeros(4000, np.float32),
+    }[name]()
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    os.environ["QASR_DEBUG_KEEP"] = "1"
+    from oracle import CONFIGS, make_weights
+    from qwen3_asr_b200 import B200AudioEncoder
+
+    cfg = CONFIGS["tiny"]
+    w = make_weights(cfg, seed=1)
+    enc = B200AudioEncoder(cfg, w, max_chunks=64)
+    yield cfg, w, enc
+    enc.close()
+
+
+# ---------------------------------------------------------------------------------------------- mel
+def test_logmel_golden_batch(tiny, golden):
+    """All golden clips in ONE ragged batch: per-clip standalone semantics must hold inside a batch."""
+    from oracle import logmel
+
+    _, _, enc = tiny
+    names = [str(n) for n in golden["mel_names"]]
+    clips = [_clip(golden, n) for n in names]
+    mel, flens = enc.logmel(clips)
+    mel = mel.cpu().numpy()
+    col = 0
+    for n, x, t in zip(names, clips, flens):
+        ref = golden[f"mel_{n}"]
+        got = mel[:, col:col + int(t)]
+        col += int(t)
+        assert got.shape == ref.shape, n
+        assert np.isfinite(got).all(), n
+        assert range_rel(got, ref) <= MEL_TOL, (n, "vs transformers golden", range_rel(got, ref))
+        assert range_rel(got, logmel(x)) <= MEL_TOL, (n, "vs f64 oracle", range_rel(got, logmel(x)))
+    assert col == mel.shape[1]
+
+
+def test_logmel_zero_clip_is_minus_1p5(tiny):
+    _, _, enc = tiny
+    mel, flens = enc.logmel([np.zeros(4000, np.float32)])
+    assert int(flens[0]) == 25
+    assert torch.all(mel == -1.5)
+
+
+def test_logmel_host_entry_point(tiny, golden):
+    _, _, enc = tiny
+    x = _clip(golden, "noise5s")
+    mel, flens = enc.logmel_host([x, x[:12345]])
+    assert list(flens) == [500, 77]
+    assert range_rel(mel[:, :500], golden["mel_noise5s"]) <= MEL_TOL
+
+
+def test_logmel_rejects_too_short_clip(tiny):
+    from qwen3_asr_b200 import QasrError
+
+    _, _, enc = tiny
+    with pytest.raises(QasrError):
+        enc.logmel([np.zeros(200, np.float32)])  # torch.stft's reflect pad raises too
+
+
+def test_logmel_edges_and_lengths(tiny):
+    """Clip lengths around the slab (16 frames) and hop boundaries, against the f64 oracle."""
+    from oracle import logmel
+    from oracle.signals import speech_like
+
+    _, _, enc = tiny
+    lens = [201, 319, 320, 2559, 2560, 2561, 2719, 2720, 16000 + 159, 160 * 33 + 80]
+    clips = [speech_like(n, 300 + i) for i, n in enumerate(lens)]
+    mel, flens = enc.logmel(clips)
+    mel = mel.cpu().numpy()
+    col = 0
+    for x, t in zip(clips, flens):
+        assert int(t) == x.shape[0] // 160
+        if t:
+            assert range_rel(mel[:, col:col + int(t)], logmel(x)) <= MEL_TOL, (x.shape[0], range_rel(mel[:, col:col + int(t)], logmel(x)))
+        col += int(t)
+
+
+# ---------------------------------------------------------------------------------------------- encoder
+def _oracle(cfg, w, mels, **kw):
+    from oracle import encoder_forward
+
+    return encoder_forward(w, cfg, mels, **kw)
+
+
+def _bf16_round(m):
+    return torch.from_numpy(np.ascontiguousarray(m)).to(torch.bfloat16).float().numpy()
+
+
+def test_conv_stem_intermediates_tiny(tiny):
+    """conv1 / conv2 / conv3 activations and the post-conv_out embeddings against torch conv2d on the same bf16 values."""
+    import torch.nn.functional as F
+    from oracle import logmel
+    from oracle.signals import speech_like
+    from qwen3_asr_b200.encoder import bf16_bits_to_f32
+
+    cfg, w, enc = tiny
+    lens = [300, 177]  # 3 full chunks; 1 full + 77-frame tail (padded to 100)
+    mels = [_bf16_round(logmel(speech_like(t * 160, 70 + i))) for i, t in enumerate(lens)]
+    packed = torch.from_numpy(np.concatenate(mels, axis=1)).cuda()
+    out = enc.encode(packed, lens)
+    torch.cuda.synchronize()
+    assert out.shape == (39 + 13 + 10, cfg.output_dim)
+
+    # torch statement, bf16 rounding after every module (the deployment's rounding points)
+    chunks = []
+    for m in mels:
+        t = m.shape[1]
+        for s in range(0, t, 100):
+            ch = np.zeros((128, 100), np.float32)
+            ch[:, : min(100, t - s)] = m[:, s:s + 100]
+            chunks.append(ch)
+    x = torch.from_numpy(np.stack(chunks))[:, None]
+    rnd = lambda v: v.to(torch.bfloat16).float()
+    acts = []
+    for i in (1, 2, 3):
+        x = rnd(F.gelu(rnd(F.conv2d(x, w[f"conv2d{i}.weight"], w[f"conv2d{i}.bias"], stride=2, padding=1))))
+        acts.append(x)
+    nc = len(chunks)
+
+    a1 = bf16_bits_to_f32(enc.debug_read("act1", max_bytes=nc * 52 * 64 * 480 * 2)).reshape(nc, 52, 64, 480)
+    ref1 = acts[0].permute(0, 3, 2, 1).numpy()  # [n, w, h, c]
+    assert np.all(a1[:, 0] == 0) and np.all(a1[:, 51] == 0), "conv1 padding columns must be zero"
+    e1 = np.abs(a1[:, 1:51] - ref1).max()
+    assert e1 <= 2 ** -7 * np.abs(ref1).max(), ("act1", e1)
+
+    a2 = bf16_bits_to_f32(enc.debug_read("act2", max_bytes=nc * 26 * 32 * 480 * 2)).reshape(nc, 26, 32, 480)
+    ref2 = acts[1].permute(0, 3, 2, 1).numpy()
+    assert np.all(a2[:, 0] == 0), "conv2 left padding column must be zero"
+    e2 = np.abs(a2[:, 1:26] - ref2).max()
+    assert e2 <= 2 ** -6 * np.abs(ref2).max(), ("act2", e2, np.abs(ref2).max())
+
+    a3 = bf16_bits_to_f32(enc.debug_read("act3", max_bytes=nc * 13 * 16 * 480 * 2)).reshape(nc, 13, 16, 480)
+    ref3 = acts[2].permute(0, 3, 2, 1).numpy()
+    e3 = np.abs(a3 - ref3).max()
+    assert e3 <= 2 ** -6 * np.abs(ref3).max(), ("act3", e3, np.abs(ref3).max())
+
+    _, _, inter = _oracle(cfg, w, mels, emulate_bf16=True, return_intermediate=True)
+    emb = bf16_bits_to_f32(enc.debug_read("embed", max_bytes=out.shape[0] * cfg.d_model * 2)).reshape(out.shape[0], cfg.d_model)
+    ee = range_rel(emb, inter["embed"].numpy())
+    assert ee <= 2 ** -6, ("embed", ee)
+
+
+def test_encoder_tiny_vs_golden_and_oracle(tiny, golden):
+    """Golden = the transformers module (fp32, window mask injected) on the same weights and clips."""
+    from oracle.signals import speech_like
+
+    cfg, w, enc = tiny
+    lens = [int(t) for t in golden["enc_tiny_lens"]]
+    clips = [speech_like(t * 160, 50 + i) for i, t in enumerate(lens)]
+    out, toks = enc.encode_pcm(clips)  # fused PCM -> mel -> encoder, ragged batch
+    out = out.float().cpu().numpy()
+    s = 0
+    for i, (t, n) in enumerate(zip(lens, toks)):
+        ref = golden[f"enc_tiny_{i}"]
+        assert int(n) == ref.shape[0] == enc.token_len(t)
+        err = range_rel(out[s:s + int(n)], ref)
+        assert err <= HID_TOL, (i, t, err)
+        s += int(n)
+    assert s == out.shape[0]
+
+
+def test_encoder_tiny_simt_path_matches(tiny, golden):
+    """The SIMT checker path (no TMA / tcgen05) through the same host plan: separates tensor-core
+    descriptor bugs from plan / layout / epilogue bugs when the previous test fails."""
+    from oracle import CONFIGS, make_weights
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import B200AudioEncoder
+
+    cfg, w, enc = tiny
+    os.environ["QASR_DEBUG_SIMT"] = "1"
+    try:
+        enc2 = B200AudioEncoder(cfg, w, max_chunks=16)
+    finally:
+        os.environ.pop("QASR_DEBUG_SIMT")
+    try:
+        lens = [177, 45]
+        clips = [speech_like(t * 160, 50 + i) for i, t in enumerate(lens)]
+        o1, _ = enc.encode_pcm(clips)
+        o2, _ = enc2.encode_pcm(clips)
+        ref, _ = _oracle(cfg, w, [_bf16_round(m) for m in _mels(enc, clips)], emulate_bf16=True)
+        e_simt = range_rel(o2.float().cpu().numpy(), ref.numpy())
+        e_tc = range_rel(o1.float().cpu().numpy(), ref.numpy())
+        assert e_simt <= HID_TOL, ("simt", e_simt)
+        assert e_tc <= HID_TOL, ("tcgen05", e_tc)
+    finally:
+        enc2.close()
+
+
+def _mels(enc, clips):
+    mel, flens = enc.logmel(clips)
+    mel = mel.cpu().numpy()
+    out, c = [], 0
+    for t in flens:
+        out.append(mel[:, c:c + int(t)])
+        c += int(t)
+    return out
+
+
+def test_encoder_batch_invariance_and_determinism(tiny):
+    """A clip's tokens must not depend on what else is in the batch (bit-exact), nor on the run."""
+    from oracle.signals import speech_like
+
+    _, _, enc = tiny
+    clips = [speech_like(t * 160, 400 + i) for i, t in enumerate((77, 300, 1056, 45, 835))]
+    out, toks = enc.encode_pcm(clips)
+    out2, _ = enc.encode_pcm(clips)
+    assert torch.equal(out, out2)
+    s = 0
+    for c, n in zip(clips, toks):
+        alone, _ = enc.encode_pcm([c])
+        assert torch.equal(out[s:s + int(n)], alone), "batching changed a clip's tokens"
+        s += int(n)
+
+
+def test_encoder_microbatch_split_is_exact(tiny):
+    """Requests larger than the handle's capacity are split at attention-window boundaries: same bits."""
+    from oracle import CONFIGS
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import B200AudioEncoder
+
+    cfg, w, enc = tiny
+    small = B200AudioEncoder(cfg, w, max_chunks=8, max_tokens=104)
+    try:
+        clips = [speech_like(t * 160, 500 + i) for i, t in enumerate((2130, 77, 950))]
+        a, ta = enc.encode_pcm(clips)
+        b, tb = small.encode_pcm(clips)
+        assert list(ta) == list(tb)
+        assert torch.equal(a, b)
+    finally:
+        small.close()
+
+
+def test_forward_signature_matches_audio_tower(tiny):
+    """forward(input_features[128, sum T], feature_lens) -> .last_hidden_state, and the hook's [1,128,T] form."""
+    from oracle import logmel
+    from oracle.signals import speech_like
+
+    _, _, enc = tiny
+    m = torch.from_numpy(logmel(speech_like(300 * 160, 9))).cuda().to(torch.bfloat16)
+    o1 = enc.forward(m, feature_lens=torch.tensor([300])).last_hidden_state
+    o2 = enc(m[None])[0]
+    assert o1.shape == (39, enc.output_dim) and torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("name", ["0.6B"])
+def test_encoder_config1_vs_golden(name, golden):
+    """BASELINE config 1: 0.6B dims, one 5 s clip, against the transformers module's fp32 output."""
+    from oracle import CONFIGS, make_weights
+    from oracle.signals import noise_clip
+    from qwen3_asr_b200 import B200AudioEncoder
+
+    cfg = CONFIGS[name]
+    w = make_weights(cfg, seed=2)
+    enc = B200AudioEncoder(cfg, w, max_chunks=64)
+    try:
+        out, toks = enc.encode_pcm([noise_clip(80000, 0)])
+        assert list(toks) == [65]
+        err = range_rel(out.float().cpu().numpy(), golden["enc_c1"])
+        assert err <= HID_TOL, err
+    finally:
+        enc.close()

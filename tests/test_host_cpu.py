@@ -1,0 +1,120 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads without a GPU and exports every
+symbol include/qasr_b200.h declares; host-only entry points agree with the golden vectors; the log-mel
+kernel's __host__ __device__ math (FFT butterflies, real-input split, filter tables), compiled for the host,
+agrees with the oracle; clip sharding is a valid deterministic partition."""
+
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from qwen3_asr_b200.build import build
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    build()
+    from qwen3_asr_b200 import load_library
+
+    return load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from qwen3_asr_b200._lib import SIGNATURES
+
+    hdr = open(os.path.join(ROOT, "include", "qasr_b200.h")).read()
+    declared = set(re.findall(r"QASR_API\s+[\w\s\*]+?\b(qasr_\w+)\s*\(", hdr))
+    assert len(declared) >= 18
+    assert declared == set(SIGNATURES), declared ^ set(SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.qasr_abi_version() == 1
+
+
+def test_token_len_matches_transformers_golden(lib, golden):
+    for t, n in zip(golden["toklen_T"], golden["toklen"]):
+        assert lib.qasr_token_len(int(t)) == int(n), int(t)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    from qwen3_asr_b200 import B200AudioEncoder, QasrError
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(QasrError):
+        B200AudioEncoder({}, {})
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from qwen3_asr_b200 import QasrError, load_library
+
+    with pytest.raises(QasrError):
+        load_library(str(tmp_path / "nope.so"))
+
+
+def test_create_rejects_bad_config_before_touching_cuda(lib):
+    import ctypes as C
+
+    from qwen3_asr_b200._lib import QasrConfig
+
+    cfg = QasrConfig(d_model=1000, encoder_layers=2, encoder_attention_heads=16, encoder_ffn_dim=4096, output_dim=2048, n_window=50,
+                     n_window_infer=800, downsample_hidden_size=480, num_mel_bins=128, max_source_positions=1500)
+    h = C.c_void_p()
+    assert lib.qasr_create(C.byref(cfg), 0, C.byref(h)) != 0
+    assert b"head_dim" in lib.qasr_last_error()
+
+
+@pytest.fixture(scope="module")
+def mel_host_bin(tmp_path_factory):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = str(tmp_path_factory.mktemp("melhost") / "mel_host_test")
+    src = os.path.join(ROOT, "tests", "host", "mel_host_test.cu")
+    mel = os.path.join(ROOT, "qwen3_asr_b200", "csrc", "mel.cu")
+    r = subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, src, mel],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+@pytest.mark.parametrize("name", ["speech2s", "odd", "tone", "english_01"])
+def test_mel_kernel_math_on_host(mel_host_bin, golden, tmp_path, name):
+    """The kernel's own butterfly / split / filter code, executed on the CPU, against the f64 oracle."""
+    from oracle.logmel import log10_mel_unclamped
+    from test_oracle_golden import _clip
+
+    x = _clip(golden, name)
+    pcm, out = str(tmp_path / "pcm.bin"), str(tmp_path / "mel.bin")
+    x.astype(np.float32).tofile(pcm)
+    r = subprocess.run([mel_host_bin, pcm, out], capture_output=True, text=True)
+    assert r.returncode == 0
+    t = x.shape[0] // 160
+    got = np.fromfile(out, dtype=np.float32).reshape(128, t)
+    ref = log10_mel_unclamped(x)
+    got = (np.maximum(got, got.max() - 8.0) + 4.0) / 4.0
+    ref = (np.maximum(ref, ref.max() - 8.0) + 4.0) / 4.0
+    assert np.abs(got - ref).max() / np.abs(ref).max() <= 1e-4
+    assert np.abs(got - golden[f"mel_{name}"]).max() / np.abs(ref).max() <= 1e-4
+
+
+def test_lpt_assign_is_a_balanced_partition():
+    from qwen3_asr_b200.synth import lpt_assign
+
+    rng = np.random.default_rng(0)
+    frames = rng.integers(100, 3000, size=230).tolist()
+    for n in (1, 2, 4, 8):
+        bins = lpt_assign(frames, n)
+        assert sorted(i for b in bins for i in b) == list(range(len(frames)))
+        loads = [sum(frames[i] for i in b) for b in bins]
+        assert max(loads) - min(loads) <= max(frames)
+        assert bins == lpt_assign(frames, n)
