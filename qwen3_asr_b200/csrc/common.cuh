@@ -37,16 +37,46 @@ void set_last_error(const std::string& msg);
 // ---- numerics ------------------------------------------------------------------------------
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// exact-erf GELU (torch F.gelu default, ACT2FN["gelu"]): 0.5 x (1 + erf(x / sqrt 2))
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// erf GELU (torch F.gelu default, ACT2FN["gelu"]): 0.5 x (1 + erf(x / sqrt 2)) = x - x q(|x|) for x >= 0, x q(|x|)
+// for x < 0, with q(a) = 0.5 erfc(a / sqrt 2) from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): branch-free,
+// 2 MUFU + ~12 FP32 ops, no cancellation in the negative tail.  Over all bf16 inputs its bf16-rounded result differs
+// from the float64 GELU in 169 of 35898 values (by 1 ulp), torch's own float32 erff path in 129 (tests/test_host_cpu.py).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float a = fabsf(x);
+  const float t = rcp_approx(fmaf(0.231641888f, a, 1.0f));          // 1 / (1 + 0.3275911 a / sqrt 2)
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);                  // 0.5 * (a5 .. a1), Horner in t
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float e = ex2_approx(a * a * -0.72134752044f);               // exp(-a^2 / 2)
+  const float q = p * t * e;
+  const float xq = x * q;
+  return x >= 0.f ? x - xq : xq;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Round two floats to bf16 and back with ONE packed conversion (F2FP, ALU pipe) + two logic ops; the scalar
+// cvt.rn.bf16.f32 (F2F) runs on the 16-lane XU pipe shared with MUFU and was a bottleneck of the GELU epilogues.
+__device__ __forceinline__ float2 bf16_round2(float a, float b) {
+  const uint32_t p = pack_bf16x2(a, b);
+  return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u));
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
 // order-preserving float <-> uint32 map for atomicMax on floats of either sign

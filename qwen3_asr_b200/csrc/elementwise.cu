@@ -2,6 +2,8 @@
 // non-causal multi-head attention of the audio encoder.  Restates
 // transformers/models/qwen3_omni_moe/modeling_qwen3_omni_moe.py: conv2d1 :649,730; LayerNorm :576,580,647;
 // attention :496-565 / eager definition :471-493 with the per-window block-diagonal structure of :676-693.
+#include <algorithm>
+
 #include "kernels.h"
 #include "common.cuh"
 
@@ -73,70 +75,91 @@ __global__ void __launch_bounds__(256) conv1_kernel(const MelT* __restrict__ mel
           xa = fmaf(wa[kh * 3 + kw], x, xa);
           xb = fmaf(wb[kh * 3 + kw], x, xb);
         }
-      const float ya = gelu_erf(bf16_round(xa)), yb = gelu_erf(bf16_round(xb));
+      const float2 xr = bf16_round2(xa, xb);
+      const float ya = gelu_erf(xr.x), yb = gelu_erf(xr.y);
       *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(h) * channels) = pack_bf16x2(ya, yb);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm over the last dim, one warp per row, fp32 statistics (two-pass in registers).
+// LayerNorm over the last dim.  A warp owns rows warp_global, warp_global + n_warps, ...; its lanes keep their
+// gamma / beta columns in registers for all rows (re-loading them per row was 4x the traffic of x itself) and the
+// next row's x is fetched while the current one is reduced.  fp32 statistics, two-pass in registers.
 // ---------------------------------------------------------------------------------------------
+constexpr int LN_WARPS = 8;
+
 template <int NV>  // NV = ceil(d / 256): 8-element vectors per lane
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows,
-                                                        int d, float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(LN_WARPS * 32, 2) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                                  int rows, int d, float eps) {
   const int lane = threadIdx.x & 31;
+  const int n_warps = gridDim.x * LN_WARPS;
+  int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const __nv_bfloat16* xr = x + static_cast<long long>(row) * d;
-  float v[NV][8];
-  float sum = 0.f;
+  float g[NV][8], b[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = (i * 32 + lane) * 8;
     if (col < d) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + col);
+      *reinterpret_cast<float4*>(&g[i][0]) = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      *reinterpret_cast<float4*>(&g[i][4]) = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+      *reinterpret_cast<float4*>(&b[i][0]) = __ldg(reinterpret_cast<const float4*>(beta + col));
+      *reinterpret_cast<float4*>(&b[i][4]) = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    }
+  }
+  uint4 nxt[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    nxt[i] = col < d ? *reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * d + col) : make_uint4(0, 0, 0, 0);
+  }
+  const float inv_d = 1.0f / d;
+  for (; row < rows; row += n_warps) {
+    float v[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
       float2 t;
-      t = unpack_bf16x2(u.x); v[i][0] = t.x; v[i][1] = t.y;
-      t = unpack_bf16x2(u.y); v[i][2] = t.x; v[i][3] = t.y;
-      t = unpack_bf16x2(u.z); v[i][4] = t.x; v[i][5] = t.y;
-      t = unpack_bf16x2(u.w); v[i][6] = t.x; v[i][7] = t.y;
+      t = unpack_bf16x2(nxt[i].x); v[i][0] = t.x; v[i][1] = t.y;
+      t = unpack_bf16x2(nxt[i].y); v[i][2] = t.x; v[i][3] = t.y;
+      t = unpack_bf16x2(nxt[i].z); v[i][4] = t.x; v[i][5] = t.y;
+      t = unpack_bf16x2(nxt[i].w); v[i][6] = t.x; v[i][7] = t.y;
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += v[i][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
     }
-  }
-  const float mean = warp_sum(sum) / d;
-  float sq = 0.f;
+    const int next_row = row + n_warps;
+    if (next_row < rows) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 8;
-    if (col < d) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; sq = fmaf(t, t, sq); }
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 8;
+        if (col < d) nxt[i] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(next_row) * d + col);
+      }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / d + eps);
-  __nv_bfloat16* orow = out + static_cast<long long>(row) * d;
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 8;
-    if (col < d) {
-      float g[8], b[8];
-      *reinterpret_cast<float4*>(g) = __ldg(reinterpret_cast<const float4*>(gamma + col));
-      *reinterpret_cast<float4*>(g + 4) = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-      *reinterpret_cast<float4*>(b) = __ldg(reinterpret_cast<const float4*>(beta + col));
-      *reinterpret_cast<float4*>(b + 4) = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
-      float y[8];
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 8;
+      if (col < d) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
-      uint4 u;
-      u.x = pack_bf16x2(y[0], y[1]); u.y = pack_bf16x2(y[2], y[3]);
-      u.z = pack_bf16x2(y[4], y[5]); u.w = pack_bf16x2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(orow + col) = u;
+        for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; sq = fmaf(t, t, sq); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+    __nv_bfloat16* orow = out + static_cast<long long>(row) * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 8;
+      if (col < d) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * g[i][j] + b[i][j];
+        uint4 u;
+        u.x = pack_bf16x2(y[0], y[1]); u.y = pack_bf16x2(y[2], y[3]);
+        u.z = pack_bf16x2(y[4], y[5]); u.w = pack_bf16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(orow + col) = u;
+      }
     }
   }
 }
@@ -150,7 +173,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 // ---------------------------------------------------------------------------------------------
 constexpr int HD = 64;
 constexpr int KV_STRIDE = 72;  // bf16 elements per smem row (144 B): conflict-free fragment + ldmatrix access
-constexpr int ATT_WARPS = 4;
+constexpr int ATT_WARPS = 8;  // a 104-token window is 7 query tiles of 16 rows: one per warp
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -175,18 +198,21 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
   const int wl16 = (wl + 15) & ~15;
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
   __nv_bfloat16* sV = sK + wl16 * KV_STRIDE;
+  __nv_bfloat16* sQ = sV + wl16 * KV_STRIDE;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ldq = 3LL * d;
   const __nv_bfloat16* base = qkv + static_cast<long long>(start) * ldq + head * HD;
 
-  // stage K, V (rows >= wl zero-filled so masked P = 0 never meets garbage)
+  // stage Q, K, V with 16-byte loads, 128 contiguous bytes per row (rows >= wl zero-filled so masked P = 0 never meets garbage)
   for (int i = tid; i < wl16 * 8; i += ATT_WARPS * 32) {
     const int r = i >> 3, c = (i & 7) * 8;
-    uint4 k = make_uint4(0, 0, 0, 0), v = make_uint4(0, 0, 0, 0);
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
     if (r < wl) {
+      q = *reinterpret_cast<const uint4*>(base + r * ldq + c);
       k = *reinterpret_cast<const uint4*>(base + r * ldq + d + c);
       v = *reinterpret_cast<const uint4*>(base + r * ldq + 2 * d + c);
     }
+    *reinterpret_cast<uint4*>(sQ + r * KV_STRIDE + c) = q;
     *reinterpret_cast<uint4*>(sK + r * KV_STRIDE + c) = k;
     *reinterpret_cast<uint4*>(sV + r * KV_STRIDE + c) = v;
   }
@@ -195,15 +221,15 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
   const int g = lane >> 2, t = lane & 3;
   for (int qt = warp; qt * 16 < wl; qt += ATT_WARPS) {
     const int r0 = qt * 16 + g, r1 = r0 + 8;
-    // Q fragments for the 4 k16 steps over head_dim
+    // Q fragments for the 4 k16 steps over head_dim (row pitch 144 B: the 32 lanes hit 32 distinct banks)
     uint32_t qa[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       const int c = ks * 16 + 2 * t;
-      qa[ks][0] = r0 < wl ? *reinterpret_cast<const uint32_t*>(base + r0 * ldq + c) : 0u;
-      qa[ks][1] = r1 < wl ? *reinterpret_cast<const uint32_t*>(base + r1 * ldq + c) : 0u;
-      qa[ks][2] = r0 < wl ? *reinterpret_cast<const uint32_t*>(base + r0 * ldq + c + 8) : 0u;
-      qa[ks][3] = r1 < wl ? *reinterpret_cast<const uint32_t*>(base + r1 * ldq + c + 8) : 0u;
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(sQ + r0 * KV_STRIDE + c);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(sQ + r1 * KV_STRIDE + c);
+      qa[ks][2] = *reinterpret_cast<const uint32_t*>(sQ + r0 * KV_STRIDE + c + 8);
+      qa[ks][3] = *reinterpret_cast<const uint32_t*>(sQ + r1 * KV_STRIDE + c + 8);
     }
     float o[8][4];
 #pragma unroll
@@ -304,12 +330,13 @@ cudaError_t launch_layernorm(const __nv_bfloat16* x, const float* gamma, const f
                              float eps, cudaStream_t stream) {
   if (rows == 0) return cudaSuccess;
   if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;
-  const int grid = (rows + 7) / 8;
+  // ~5 rows per warp at the C2 batch (12480 rows): enough rows to amortise the gamma/beta registers, enough warps to fill the chip
+  const int grid = std::max(1, std::min((rows + LN_WARPS - 1) / LN_WARPS, 2 * kNumSMs));
   const int nv = (d + 255) / 256;
-  if (nv <= 1) layernorm_kernel<1><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
-  else if (nv <= 2) layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
-  else if (nv <= 4) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
-  else layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  if (nv <= 1) layernorm_kernel<1><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  else if (nv <= 2) layernorm_kernel<2><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  else if (nv <= 4) layernorm_kernel<4><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
+  else layernorm_kernel<8><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
   return cudaGetLastError();
 }
 
@@ -318,7 +345,7 @@ cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out
   if (n_win == 0) return cudaSuccess;
   if (d != heads * HD) return cudaErrorInvalidValue;
   const int wl16 = (max_win_len + 15) & ~15;
-  const size_t smem = static_cast<size_t>(2) * wl16 * KV_STRIDE * sizeof(__nv_bfloat16);
+  const size_t smem = static_cast<size_t>(3) * wl16 * KV_STRIDE * sizeof(__nv_bfloat16);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;

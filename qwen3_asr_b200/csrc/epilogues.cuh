@@ -39,6 +39,27 @@ __device__ __forceinline__ void load16_f32(const float* src, float (&v)[16]) {
 
 enum EpiAct : int { ACT_NONE = 0, ACT_GELU = 1 };
 
+struct NoPrefetch {};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); v[0] = t.x; v[1] = t.y;
+  t = unpack_bf16x2(u.y); v[2] = t.x; v[3] = t.y;
+  t = unpack_bf16x2(u.z); v[4] = t.x; v[5] = t.y;
+  t = unpack_bf16x2(u.w); v[6] = t.x; v[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
+
+// The GEMM kernel computes y = act(bf16(acc + bias[n])) per element (zero for rows that are not live), stages it as
+// bf16 and then hands 8 consecutive columns at a time to finish(), which stores them (after an optional addend).
+
 // out[m, n] = bf16( act( bf16(acc + bias[n]) ) (+ residual[m, n]) )      -- nn.Linear (+GELU) (+ residual add)
 template <int ACT, bool RESIDUAL>
 struct EpiLinear {
@@ -47,28 +68,28 @@ struct EpiLinear {
   const __nv_bfloat16* residual;   // [M, ldo] (may alias out) when RESIDUAL
   long long ldo;
   int m_valid, n_valid;
-  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[16]) const {
-    if (m >= m_valid || n0 >= n_valid) return;
-    float v[16], b[16];
-    if (bias != nullptr) {
-      load16_f32(bias + n0, b);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) b[j] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float x = bf16_round(acc[j] + b[j]);
-      if (ACT == ACT_GELU) x = gelu_erf(x);
-      v[j] = x;
-    }
+  struct Prefetch { uint4 r; };
+  __device__ __forceinline__ const float* bias_ptr() const { return bias; }
+  __device__ __forceinline__ int n_cols() const { return n_valid; }
+  __device__ __forceinline__ bool row_live(int) const { return true; }
+  __device__ __forceinline__ float act(float v) const { return ACT == ACT_GELU ? gelu_erf(v) : v; }
+  __device__ __forceinline__ long long offset(int m, int n) const { return (m < m_valid && n < n_valid) ? m * ldo + n : -1; }
+  __device__ __forceinline__ Prefetch prefetch(int, int, long long off) const {
+    Prefetch p;
+    if (RESIDUAL) p.r = *reinterpret_cast<const uint4*>(residual + off);
+    return p;
+  }
+  __device__ __forceinline__ void finish(long long off, const uint4& y, const Prefetch& p) const {
     if (RESIDUAL) {
-      float r[16];
-      load16_bf16(residual + m * ldo + n0, r);
+      float a[8], r[8];
+      unpack8(y, a);
+      unpack8(p.r, r);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = bf16_round(v[j]) + r[j];
+      for (int j = 0; j < 8; ++j) a[j] += r[j];
+      *reinterpret_cast<uint4*>(out + off) = pack8(a);
+    } else {
+      *reinterpret_cast<uint4*>(out + off) = y;
     }
-    store16_bf16(out + m * ldo + n0, v);
   }
 };
 
@@ -86,23 +107,26 @@ struct EpiConv {
   int max_w;               // 25 / 13
   int out_pitch, out_off;  // destination column = chunk * out_pitch + out_off + ow
   int n_chunks, c;         // c = channels (480)
-  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[16]) const {
-    if (n0 >= c) return;
+  typedef NoPrefetch Prefetch;
+  __device__ __forceinline__ const float* bias_ptr() const { return bias; }
+  __device__ __forceinline__ int n_cols() const { return c; }
+  __device__ __forceinline__ bool row_live(int m) const {
+    const int g = m / hc;
+    const int chunk = g / slots, ow = g - chunk * slots;
+    return chunk < n_chunks && ow < __ldg(width + chunk);
+  }
+  __device__ __forceinline__ float act(float v) const { return gelu_erf(v); }
+  __device__ __forceinline__ long long offset(int m, int n) const {
+    if (n >= c) return -1;
     const int g = m / hc, h = m - g * hc;
     const int chunk = g / slots, ow = g - chunk * slots;
-    if (chunk >= n_chunks || ow >= max_w) return;
-    float v[16];
-    if (ow < __ldg(width + chunk)) {
-      float b[16];
-      load16_f32(bias + n0, b);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(bf16_round(acc[j] + b[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 0.f;
-    }
+    if (chunk >= n_chunks || ow >= max_w) return -1;
     const long long col = static_cast<long long>(chunk) * out_pitch + out_off + ow;
-    store16_bf16(out + (col * hc + h) * c + n0, v);
+    return (col * hc + h) * c + n;
+  }
+  __device__ __forceinline__ Prefetch prefetch(int, int, long long) const { return Prefetch(); }
+  __device__ __forceinline__ void finish(long long off, const uint4& y, const Prefetch&) const {
+    *reinterpret_cast<uint4*>(out + off) = y;
   }
 };
 
@@ -114,16 +138,29 @@ struct EpiConvOut {
   const int* row_token;    // [m_valid]
   int tok_per_chunk;       // 13
   int d, m_valid;
-  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[16]) const {
-    if (m >= m_valid || n0 >= d) return;
+  struct Prefetch { float4 a, b; };
+  __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
+  __device__ __forceinline__ int n_cols() const { return d; }
+  __device__ __forceinline__ bool row_live(int) const { return true; }
+  __device__ __forceinline__ float act(float v) const { return v; }
+  __device__ __forceinline__ long long offset(int m, int n) const {
+    if (m >= m_valid || n >= d) return -1;
     const int tok = __ldg(row_token + m);
-    if (tok < 0) return;
-    const int t = m % tok_per_chunk;
-    float p[16], v[16];
-    load16_f32(pe + t * d + n0, p);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = bf16_round(acc[j]) + p[j];
-    store16_bf16(out + static_cast<long long>(tok) * d + n0, v);
+    return tok < 0 ? -1 : static_cast<long long>(tok) * d + n;
+  }
+  __device__ __forceinline__ Prefetch prefetch(int m, int n, long long) const {
+    const float* p = pe + (m % tok_per_chunk) * d + n;
+    Prefetch r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+  }
+  __device__ __forceinline__ void finish(long long off, const uint4& y, const Prefetch& p) const {
+    float a[8];
+    unpack8(y, a);
+    a[0] += p.a.x; a[1] += p.a.y; a[2] += p.a.z; a[3] += p.a.w;
+    a[4] += p.b.x; a[5] += p.b.y; a[6] += p.b.z; a[7] += p.b.w;
+    *reinterpret_cast<uint4*>(out + off) = pack8(a);
   }
 };
 

@@ -91,7 +91,7 @@ cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc
 
 template <class ALoad, class Epi>
 cudaError_t launch_simt(const ALoad& aload, const __nv_bfloat16* b, long long ldb, int m, int n, int k, const Epi& epi, cudaStream_t stream) {
-  const long long items = static_cast<long long>(m) * (n / 16);
+  const long long items = static_cast<long long>(m) * (n / 8);
   if (items <= 0) return cudaSuccess;
   const int threads = 128;
   const long long blocks = (items + threads - 1) / threads;

@@ -12,7 +12,9 @@
 //   warp 0 lane 0 : TMA producer   -- cp.async.bulk.tensor into a kStages-deep 128B-swizzled ring
 //   warp 1 lane 0 : MMA issuer     -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage
 //   warp 2        : TMEM allocator -- 512 columns = two accumulator stages
-//   warps 4..7    : epilogue       -- tcgen05.ld 32 lanes x 32b, fused bias/GELU/residual/... -> bf16
+//   warps 4..11   : epilogue       -- two warps per TMEM lane quarter, 64-column panels: tcgen05.ld -> bias (from
+//                                     smem) / activation -> bf16 -> swizzled smem staging -> coalesced 128-byte row
+//                                     segments to global (+ residual / positional addend, prefetched)
 // Pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) mbarriers, so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
@@ -27,8 +29,12 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 384
+constexpr int kPanel = 64;            // epilogue panel: 64 bf16 columns = one 128-byte row segment
+constexpr int kStagingBytes = 32 * kPanel * 2;  // per epilogue warp
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage (2 stages)
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -72,16 +78,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (-> a CUDA error the host reports) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
-      printf("qasr tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+// One copy per waiting role, each on its own source line, so profiler samples attribute to the role.
+#define QASR_DEFINE_MBAR_WAIT(name)                                                                      \
+  __device__ __forceinline__ void name(uint64_t* bar, uint32_t parity) {                                 \
+    if (mbar_try_wait(bar, parity)) return;                                                              \
+    const long long t0 = clock64();                                                                      \
+    while (!mbar_try_wait(bar, parity)) {                                                                \
+      if (clock64() - t0 > 8000000000LL) { /* ~4 s at 2 GHz */                                           \
+        printf("qasr tc_gemm: " #name " timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);     \
+        __trap();                                                                                        \
+      }                                                                                                  \
+    }                                                                                                    \
   }
-}
+QASR_DEFINE_MBAR_WAIT(wait_smem_empty)  // TMA producer: stage freed by the MMAs that read it
+QASR_DEFINE_MBAR_WAIT(wait_smem_full)   // MMA issuer: TMA bytes of the stage have landed
+QASR_DEFINE_MBAR_WAIT(wait_tmem_empty)  // MMA issuer: epilogue has drained the accumulator stage
+QASR_DEFINE_MBAR_WAIT(wait_tmem_full)   // epilogue: the tile's last MMA has completed
+#undef QASR_DEFINE_MBAR_WAIT
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -152,18 +165,35 @@ template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;               // [kEpiWarps][32 rows][128 B]
+  static constexpr int BIAS_OFFSET = STAGING_OFFSET + kEpiWarps * kStagingBytes;  // float [2][256]
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * 256 * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
-  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // +1024: manual alignment slack
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
 template <int BN>
 constexpr int default_stages() { return BN > 192 ? 4 : (BN > 128 ? 4 : 6); }
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
-// The kernel.  Epi::operator()(row, col0, const float (&acc)[16]) consumes 16 consecutive columns
-// of one accumulator row; it does its own bounds/validity checks.
+// The kernel.  The epilogue functor (epilogues.cuh) supplies:
+//   bias_ptr()            per-column fp32 vector added to the accumulator (or nullptr), n_cols() its length
+//   row_live(m)           false -> the whole output row is written as zeros (conv padding columns)
+//   act(v)                applied to bf16(acc + bias)
+//   offset(m, n)          element offset of 8 consecutive output columns, or -1 to skip them
+//   prefetch / finish     optional post-rounding addend (residual, positional table) and the final store
 // ---------------------------------------------------------------------------------------------
 template <int BN, int STAGES, int AMODE, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -172,8 +202,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(BN <= kAccStride, "an accumulator stage is kAccStride TMEM columns");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned stage bases
+    if (threadIdx.x == 0) printf("qasr tc_gemm: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* full_bar = bars;                      // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;            // [STAGES] MMA -> TMA
@@ -196,7 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one elected lane of each epilogue warp
+      mbar_init(&tmem_empty_bar[i], kEpiWarps);  // one elected lane of each epilogue warp
     }
     fence_barrier_init();
   }
@@ -215,7 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m_blk = tile / shape.n_tiles;
         const int n_blk = tile % shape.n_tiles;
         for (int kb = 0; kb < shape.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          wait_smem_empty(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -244,11 +277,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        wait_tmem_empty(&tmem_empty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kAccStride);
         for (int kb = 0; kb < shape.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          wait_smem_full(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -267,25 +300,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
-    const int q = warp - kEpiWarp0;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = warp - kEpiWarp0;
+    const int q = ew & 3;       // == warp % 4: the TMEM lane quarter this warp may read
+    const int half = ew >> 2;   // the two warps of a quarter take alternate 64-column panels
+    const int et = threadIdx.x - kEpiWarp0 * 32;
+    const uint32_t stage_base = smem_u32(smem + L::STAGING_OFFSET + ew * kStagingBytes);
+    float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+    constexpr int NP = (BN + kPanel - 1) / kPanel;
+    const int sub = lane >> 3, ch = lane & 7;  // phase B: row within a 4-row group, 16-byte chunk of the row segment
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / shape.n_tiles;
       const int n_blk = tile % shape.n_tiles;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      mbar_wait(&tmem_full_bar[as], aphase);
+      {  // this tile's bias columns -> smem (overlaps the tile's MMAs)
+        const float* bp = epi.bias_ptr();
+        const int n = n_blk * BN + et;
+        float b = 0.f;
+        if (et < BN && bp != nullptr && n < epi.n_cols()) b = __ldg(bp + n);
+        if (et < 256) bias_s[as * 256 + et] = b;
+      }
+      named_bar_sync(1, kEpiThreads);
+      wait_tmem_full(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const bool live = epi.row_live(row0 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld16(taddr + c, v);
-        if (c + 16 < BN) tmem_ld16(taddr + c + 16, v + 16);
+      for (int p = half; p < NP; p += 2) {
+        const int c0 = p * kPanel;
+        const int ncols = BN - c0 < kPanel ? BN - c0 : kPanel;
+        // destinations of phase B + prefetch of the post-rounding addend (hidden behind phase A)
+        long long offs[8];
+        typename Epi::Prefetch pre[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = row0 + i * 4 + sub;
+          const int n = n_blk * BN + c0 + ch * 8;
+          offs[i] = ch * 8 < ncols ? epi.offset(m, n) : -1;
+          if (offs[i] >= 0) pre[i] = epi.prefetch(m, n, offs[i]);
+        }
+        // phase A: TMEM -> registers -> bias / activation -> bf16 -> staging (row = lane, 16-byte chunks XOR-swizzled)
+        uint32_t v[kPanel];
+#pragma unroll
+        for (int g = 0; g < kPanel / 16; ++g)
+          if (g * 16 < ncols) tmem_ld16(taddr + c0 + g * 16, v + g * 16);
         tmem_ld_wait();
-        epi(row, n_blk * BN + c, reinterpret_cast<const float(&)[16]>(v[0]));
-        if (c + 16 < BN) epi(row, n_blk * BN + c + 16, reinterpret_cast<const float(&)[16]>(v[16]));
+        const float* bs = bias_s + as * 256 + c0;
+#pragma unroll
+        for (int j = 0; j < kPanel / 8; ++j) {
+          if (j * 8 < ncols) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bs + j * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bs + j * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float2 r = bf16_round2(__uint_as_float(v[j * 8 + e]) + bb[e], __uint_as_float(v[j * 8 + e + 1]) + bb[e + 1]);
+              o[e] = live ? epi.act(r.x) : 0.f;
+              o[e + 1] = live ? epi.act(r.y) : 0.f;
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2(o[0], o[1]);
+            pk.y = pack_bf16x2(o[2], o[3]);
+            pk.z = pack_bf16x2(o[4], o[5]);
+            pk.w = pack_bf16x2(o[6], o[7]);
+            st_shared_v4(stage_base + lane * 128 + ((j ^ (lane & 7)) << 4), pk);
+          }
+        }
+        __syncwarp();
+        // phase B: each instruction moves four complete 128-byte row segments
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (offs[i] >= 0) {
+            const int r = i * 4 + sub;
+            const uint4 sv = ld_shared_v4(stage_base + r * 128 + ((ch ^ (r & 7)) << 4));
+            epi.finish(offs[i], sv, pre[i]);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -329,19 +423,32 @@ struct ALoadConv {
 template <class ALoad, class Epi>
 __global__ void gemm_simt_kernel(ALoad aload, const __nv_bfloat16* __restrict__ b, long long ldb, int m_rows, int n, int k, Epi epi) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const int n_chunks = n / 16;
-  const int m = static_cast<int>(idx / n_chunks);
-  const int n0 = static_cast<int>(idx % n_chunks) * 16;
+  const int n_groups = n / 8;
+  const int m = static_cast<int>(idx / n_groups);
+  const int n0 = static_cast<int>(idx % n_groups) * 8;
   if (m >= m_rows) return;
-  float acc[16];
+  const long long off = epi.offset(m, n0);
+  if (off < 0) return;
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (int kk = 0; kk < k; ++kk) {
     const float av = aload(m, kk);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = fmaf(av, __bfloat162float(b[(n0 + j) * ldb + kk]), acc[j]);
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(av, __bfloat162float(b[(n0 + j) * ldb + kk]), acc[j]);
   }
-  epi(m, n0, acc);
+  const float* bp = epi.bias_ptr();
+  const bool live = epi.row_live(m);
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const float2 r = bf16_round2(acc[j] + (bp != nullptr ? bp[n0 + j] : 0.f), acc[j + 1] + (bp != nullptr ? bp[n0 + j + 1] : 0.f));
+    const float y0 = live ? epi.act(r.x) : 0.f;
+    const float y1 = live ? epi.act(r.y) : 0.f;
+    pk[j / 2] = pack_bf16x2(y0, y1);
+  }
+  const typename Epi::Prefetch pre = epi.prefetch(m, n0, off);
+  epi.finish(off, make_uint4(pk[0], pk[1], pk[2], pk[3]), pre);
 }
 
 }  // namespace tc
