@@ -290,3 +290,144 @@ def test_encoder_config1_vs_golden(name, golden):
         assert err <= HID_TOL, err
     finally:
         enc.close()
+
+
+# ---------------------------------------------------------------------------------------------- boundary
+def test_hook_with_transformers_audio_tower(monkeypatch):
+    """The server hook with the REAL CUDA backend behind it: a fake SDK wrapper around the transformers
+    Qwen3OmniMoeAudioEncoder (the class the reference's audio_tower is), bf16 on the GPU.  The patched call must
+    return what the torch module returns (window mask injected) within bf16 tolerance."""
+    import types
+
+    from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeAudioEncoderConfig
+    from transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe import Qwen3OmniMoeAudioEncoder
+
+    from oracle import CONFIGS, logmel, make_weights
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import server_hook
+
+    cfg = CONFIGS["tiny"]
+    hc = Qwen3OmniMoeAudioEncoderConfig(
+        num_mel_bins=128, encoder_layers=cfg.layers, encoder_attention_heads=cfg.heads, encoder_ffn_dim=cfg.ffn,
+        d_model=cfg.d_model, output_dim=cfg.output_dim, n_window=50, n_window_infer=800, conv_chunksize=500,
+        downsample_hidden_size=480, max_source_positions=1500, activation_function="gelu", scale_embedding=False,
+        dropout=0.0, attention_dropout=0.0, activation_dropout=0.0)
+    hc._attn_implementation = "eager"
+    tower = Qwen3OmniMoeAudioEncoder(hc).eval()
+    tower.load_state_dict(make_weights(cfg, seed=1), strict=False)
+    tower = tower.to("cuda", torch.bfloat16)
+    for layer in tower.layers:  # the reference deployment gets the window mask from flash-attn varlen
+        orig = layer.forward
+
+        def fwd(hidden_states, cu_seqlens, attention_mask=None, _orig=orig, **kw):
+            return _orig(hidden_states, cu_seqlens, attention_mask=tower._prepare_attention_mask(hidden_states, cu_seqlens), **kw)
+
+        layer.forward = fwd
+
+    t = 1056
+    feats = torch.from_numpy(logmel(speech_like(t * 160, 21))).to("cuda", torch.bfloat16)
+    lens = torch.tensor([t], device="cuda")
+
+    class SDK:
+        def __init__(self):
+            self.model = types.SimpleNamespace(thinker=types.SimpleNamespace(audio_tower=tower))
+
+        def transcribe(self, *_a, **_k):
+            with torch.inference_mode():
+                return self.model.thinker.audio_tower.forward(feats, feature_lens=lens).last_hidden_state
+
+    m = SDK()
+    ref = m.transcribe().float()
+    monkeypatch.setenv("B200_ENCODER", "1")
+    try:
+        assert server_hook.try_load_b200_encoder(m) == 1
+        got = server_hook.run_transcribe(m, m.transcribe, cuda_stream=torch.cuda.Stream()).float()
+        assert got.shape == ref.shape == (137, cfg.output_dim)
+        # both sides are bf16 pipelines with different accumulation orders
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err <= 2 * HID_TOL, err
+        again = m.transcribe().float()
+        assert torch.equal(again, ref), "forward must be restored after the call"
+    finally:
+        server_hook.unload()
+
+
+def test_feature_extractor_dropin_vs_whisper_feature_extractor(tiny):
+    from transformers import WhisperFeatureExtractor
+
+    from oracle.signals import speech_like
+    from qwen3_asr_b200.frontend import B200FeatureExtractor
+
+    _, _, enc = tiny
+    fe = WhisperFeatureExtractor(feature_size=128)
+    mine = B200FeatureExtractor(enc)
+    clips = [speech_like(48000, 31), speech_like(16000 * 2 + 800, 32)]
+    out = mine(clips, sampling_rate=16000, padding=True, truncation=False, return_attention_mask=True, return_tensors="pt")
+    assert out["input_features"].shape == (2, 128, 300) and out["attention_mask"].shape == (2, 300)
+    assert out["attention_mask"].sum(1).tolist() == [300, 205]
+    for i, c in enumerate(clips):  # reference semantics: one clip per request
+        ref = fe(c, sampling_rate=16000, padding=True, truncation=False, return_attention_mask=True, return_tensors="np")
+        n = int(ref["attention_mask"][0].sum())
+        got = out["input_features"][i, :, :n].cpu().numpy()
+        assert range_rel(got, ref["input_features"][0][:, :n]) <= MEL_TOL
+
+
+# ---------------------------------------------------------------------------------------------- workloads
+def test_ws_window_batch_c3_shape_vs_oracle(tiny):
+    """BASELINE config 3 in miniature: a ragged batch of WebSocket windows (0.45 s .. 6 s, some with the 600 ms
+    flush pad, int16-quantised and band-passed as server.py:1335-1338 does) against the fp32 oracle."""
+    from oracle.signals import config_clips
+
+    cfg, w, enc = tiny
+    clips = config_clips(3, limit=24)
+    out, toks = enc.encode_pcm(clips)
+    mels = [_bf16_round(m) for m in _mels(enc, clips)]
+    ref, ref_toks = _oracle(cfg, w, mels)
+    assert list(toks) == list(ref_toks)
+    assert range_rel(out.float().cpu().numpy(), ref.numpy()) <= HID_TOL
+
+
+def test_silence_split_segments_c4_shape_sharded(tiny):
+    """BASELINE config 4 in miniature: variable-length segments sharded by LPT over 2 'ranks'; the union of the
+    shards' outputs must equal the unsharded run bit for bit (clips are independent)."""
+    from oracle.signals import config_clips
+    from qwen3_asr_b200.synth import lpt_assign
+
+    _, _, enc = tiny
+    clips = config_clips(4, limit=9)
+    full, toks = enc.encode_pcm(clips)
+    starts = np.concatenate([[0], np.cumsum(toks)])
+    for shard in lpt_assign([c.shape[0] // 160 for c in clips], 2):
+        part, ptoks = enc.encode_pcm([clips[i] for i in shard])
+        s = 0
+        for i, n in zip(shard, ptoks):
+            assert torch.equal(part[s:s + int(n)], full[int(starts[i]):int(starts[i + 1])])
+            s += int(n)
+
+
+def test_full_size_properties_1p7b():
+    """At BASELINE.json's full model size (1.7B dims, 30 s clips) the oracle is too slow for a unit test: check
+    size-independent properties instead -- determinism, batch invariance, micro-batch invariance, token counts,
+    finiteness -- plus one 30 s clip against the fp32 oracle."""
+    from oracle import CONFIGS, make_weights
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import B200AudioEncoder
+
+    cfg = CONFIGS["1.7B"]
+    w = make_weights(cfg, seed=3)
+    enc = B200AudioEncoder(cfg, w, max_chunks=128)
+    try:
+        clips = [speech_like(480000, 600 + i) for i in range(6)]
+        a, toks = enc.encode_pcm(clips)          # 180 chunks -> split into two micro-batches
+        assert list(toks) == [390] * 6 and a.shape == (2340, 2048)
+        assert torch.isfinite(a.float()).all()
+        b, _ = enc.encode_pcm(clips)
+        assert torch.equal(a, b)
+        alone, _ = enc.encode_pcm(clips[4:5])
+        assert torch.equal(alone, a[4 * 390:5 * 390])
+        mel = _bf16_round(_mels(enc, clips[:1])[0])
+        ref, _ = _oracle(cfg, w, [mel])
+        err = range_rel(a[:390].float().cpu().numpy(), ref.numpy())
+        assert err <= HID_TOL, err
+    finally:
+        enc.close()
