@@ -49,15 +49,19 @@ def is_fresh() -> bool:
     return all(os.path.getmtime(d) <= t for d in _deps() if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and is_fresh():
+def build(force: bool = False, verbose: bool = False, variant: str | None = None, defines: tuple[str, ...] = ()) -> str:
+    """Default: the product library.  `variant` + `defines` build an A/B copy (libqasr_<variant>.so) with extra -D flags;
+    tools/ab.sh selects it through QASR_B200_LIB."""
+    lib_path = LIB_PATH if variant is None else os.path.join(HERE, f"libqasr_{variant}.so")
+    obj_dir = OBJ_DIR if variant is None else os.path.join(OBJ_DIR, variant)
+    if variant is None and not force and is_fresh():
         return LIB_PATH
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -69,13 +73,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "--cudart", "static", "-o", LIB_PATH, *objs, "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
+    cmd = [nvcc, "-shared", "--cudart", "static", "-o", lib_path, *objs, "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    # python -m qwen3_asr_b200.build [--force] [-v] [--variant NAME -DX=1 ...]
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, defines=tuple(a for a in sys.argv if a.startswith("-D")))
     print(path)

@@ -49,7 +49,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // erf GELU (torch F.gelu default, ACT2FN["gelu"]): 0.5 x (1 + erf(x / sqrt 2)) = x - x q(|x|) for x >= 0, x q(|x|)
-// for x < 0, with q(a) = 0.5 erfc(a / sqrt 2) from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): branch-free,
+// for x < 0 (together: relu(x) - |x| q), with q(a) = 0.5 erfc(a / sqrt 2) from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): branch-free,
 // 2 MUFU + ~12 FP32 ops, no cancellation in the negative tail.  Over all bf16 inputs its bf16-rounded result differs
 // from the float64 GELU in 169 of 35898 values (by 1 ulp), torch's own float32 erff path in 129 (tests/test_host_cpu.py).
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -61,8 +61,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, t, 0.127414796f);
   const float e = ex2_approx(a * a * -0.72134752044f);               // exp(-a^2 / 2)
   const float q = p * t * e;
-  const float xq = x * q;
-  return x >= 0.f ? x - xq : xq;
+  return fmaf(-a, q, fmaxf(x, 0.f));                                 // relu(x) - |x| q: no predicate, no select
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

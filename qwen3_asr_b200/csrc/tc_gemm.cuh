@@ -112,6 +112,18 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// One lane of a converged warp (elect.sync): ptxas then knows the guarded region runs on exactly one lane and issues
+// the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of serialising over "active lanes".
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -241,61 +253,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / shape.n_tiles;
-        const int n_blk = tile % shape.n_tiles;
-        for (int kb = 0; kb < shape.num_kb; ++kb) {
-          wait_smem_empty(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / shape.n_tiles;
+      const int n_blk = tile % shape.n_tiles;
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < shape.num_kb; ++kb) {
+        wait_smem_empty(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if constexpr (AMODE == A_LINEAR) {
             tma_load_2d(sa, &tmA, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
           } else {
-            const int tap = kb / shape.kb_per_tap;
-            const int cb = kb - tap * shape.kb_per_tap;
             const int kh = tap / 3, kw = tap - kh * 3;
             // input column = 2 * (global output column) + kw (left zero column is part of the layout),
             // input row    = 2 * (output row) + kh - 1    (row -1 is out of bounds -> TMA zero fill)
             tma_load_3d(sa, &tmA, cb * BLOCK_K, kh - 1, 2 * (m_blk * shape.gt) + kw, &full_bar[stage]);
           }
           tma_load_2d(sb, &tmB, kb * BLOCK_K, n_blk * BN, &full_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++cb == shape.kb_per_tap) { cb = 0; ++tap; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-        const int as = iter & 1;
-        const uint32_t aphase = (iter >> 1) & 1;
-        wait_tmem_empty(&tmem_empty_bar[as], aphase ^ 1);
+    // The whole warp walks the pipeline (converged waits); one elected lane issues.  Descriptor bases of the ring's
+    // stages are loop invariants; the per-k advance (16 elements = 32 bytes inside the 128B swizzle atom) is +2 in
+    // the >>4 address field.
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
+    const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem));
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      wait_tmem_empty(&tmem_empty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kAccStride);
+      for (int kb = 0; kb < shape.num_kb; ++kb) {
+        wait_smem_full(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kAccStride);
-        for (int kb = 0; kb < shape.num_kb; ++kb) {
-          wait_smem_full(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sb);
+        const uint64_t da = desc0 + static_cast<uint64_t>((stage * L::STAGE_BYTES) >> 4);
+        const uint64_t db = da + static_cast<uint64_t>(A_STAGE_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 elements = 32 bytes along K inside the 128B swizzle atom: +2 in the >>4 address field
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          }
           umma_commit(&empty_bar[stage]);
           if (kb == shape.num_kb - 1) umma_commit(&tmem_full_bar[as]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= kEpiWarp0) {
