@@ -298,7 +298,7 @@ def main():
             m = mel_prof["logmel"]
             fin = mel_prof.get("logmel_finish", {"ms": 0.0})
             gbs = m["work"] / ((m["ms"] + fin["ms"]) / 1e3) / 1e9
-            roofline_mel = {"bound": "hbm", "kernel": "logmel_kernel + logmel_finish_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"],
+            roofline_mel = {"bound": "hbm", "kernel": "logmel_kernel (persistent, ticketed frame + clamp items)", "achieved": gbs, "peak": peaks["hbm_gbs"],
                             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
                             "algorithmic_bytes_per_launch": m["work"] / m["launches"], "avg_launch_ms": (m["ms"] + fin["ms"]) / m["launches"],
                             "workload": "8 x C2 batch (256 x 30 s): 491 MB PCM in, 393 MB log-mel out, >> L2", "traffic": None,

@@ -11,21 +11,14 @@
 namespace qasr {
 
 // ---- log-mel (mel.cu) ----------------------------------------------------------------------
-// slab table entry: one CTA = FB frames of one clip
-struct MelSlab {
-  int clip;          // clip index (per-clip max slot)
-  int frame0;        // first frame of the slab within the clip
-  int n_frames;      // valid frames in the slab (<= FB)
-  int n_samples;     // clip length in samples
-  long long pcm_off; // clip start in the packed PCM buffer
-  long long col0;    // clip start column in the packed mel
-};
-void build_mel_tables(mel::Tables* host_tables);
-cudaError_t launch_logmel(const float* pcm, const MelSlab* slabs, int n_slabs, const mel::Tables* tables,
-                          float* mel_out, long long mel_ld, unsigned int* clip_max, cudaStream_t stream);
-// clip_cols: [n_clips + 1] column offsets of each clip in the packed mel
-cudaError_t launch_logmel_finish(float* mel_out, long long mel_ld, const long long* clip_cols, int n_clips,
-                                 const unsigned int* clip_max, cudaStream_t stream);
+// build_mel_tables returns false if the computed filter-bank structure differs from the compiled-in one
+// (mel_structure.inc); upload_mel_constants copies the mel weights into constant memory of the current device.
+bool build_mel_tables(mel::Tables* host_tables);
+cudaError_t upload_mel_constants(const mel::Tables* host_tables);
+// One persistent kernel over `items` (mel::Item, device).  counters: 1 + 2 * n_clips uint32 (ticket, per-clip done, per-clip max),
+// zeroed by the launcher on `stream`.
+cudaError_t launch_logmel(const float* pcm, const mel::Item* items, int n_items, const mel::Tables* tables, float* mel_out,
+                          long long mel_ld, unsigned int* counters, int n_clips, int num_sms, cudaStream_t stream);
 
 // ---- conv1 (elementwise.cu) ------------------------------------------------------------------
 struct ChunkDesc {

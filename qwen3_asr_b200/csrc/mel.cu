@@ -1,4 +1,16 @@
-// Log-mel kernels.  See mel.cuh for the math; this file holds the CTA-level choreography.
+// Log-mel kernel: one persistent kernel, work items claimed through a global ticket (see mel.cuh for the math).
+//
+// Per item of FB = 32 frames (256 threads, 2 CTAs per SM):
+//   load     PCM slab -> smem rows of one hop (160 samples, pitch 176), reflect padding by index mirroring
+//   stage 1  thread = (frame, j): 25 strided samples x window -> real 25-point DFT in registers -> 13 complex to the
+//            exchange buffer E (XOR-swizzled 16-byte chunks: conflict-free for the 8-byte writes and the 16-byte reads)
+//   stage 2  thread = (frame, k1): 16 complex from E -> twiddle -> 16-point FFT in registers -> |X|^2 -> P[frame][bin]
+//   mel      warp = a group of filters (fully unrolled from the compiled-in structure, weights from constant memory),
+//            lane = frame: log10, raw value to HBM (128 B per warp and filter), per-clip max via atomicMax
+// The max-8 clamp needs the whole clip's max, so it runs as later work items of the same kernel (kind 1) that wait on
+// the clip's done counter and rewrite tiles that are still L2-resident; tickets are handed out in list order, every
+// item a clamp waits for has a smaller ticket and is therefore already running or finished -> no deadlock, no second
+// kernel, and the log-mel makes one trip to DRAM.
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -7,17 +19,24 @@
 
 namespace qasr {
 
+namespace {
+__constant__ float c_mel_fw[mel::MAX_NNZ];
+}
+
 // Host: constants in double, rounded once.  Filter bank follows transformers/audio_utils.py:263-332,
 // 356-375, 453-544 (Slaney scale, Slaney norm, 0..8000 Hz, 201 bins, 128 filters), cast f64 -> f32 as
-// at feature_extraction_whisper.py:152.
-void build_mel_tables(mel::Tables* t) {
+// at feature_extraction_whisper.py:152.  Returns false if the computed sparsity structure differs from
+// the compiled-in one (mel_structure.inc).
+bool build_mel_tables(mel::Tables* t) {
   using namespace mel;
   std::memset(t, 0, sizeof(Tables));
   const double PI = 3.14159265358979323846;
-  for (int k = 0; k < N_FFT; ++k) {
-    t->w400[k] = make_float2(static_cast<float>(std::cos(2.0 * PI * k / N_FFT)), static_cast<float>(-std::sin(2.0 * PI * k / N_FFT)));
-    t->window[k] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * PI * k / N_FFT));
-  }
+  for (int k = 0; k < N_FFT; ++k) t->window[k] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * PI * k / N_FFT));
+  for (int k1 = 0; k1 < K1; ++k1)
+    for (int j = 0; j < 16; ++j) {
+      const double a = 2.0 * PI * ((k1 * j) % N_FFT) / N_FFT;
+      t->tw[k1][j] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(-std::sin(a)));
+    }
   auto hz_to_mel = [](double f) { return f >= 1000.0 ? 15.0 + std::log(f / 1000.0) * (27.0 / std::log(6.4)) : 3.0 * f / 200.0; };
   auto mel_to_hz = [](double m) { return m >= 15.0 ? 1000.0 * std::exp((std::log(6.4) / 27.0) * (m - 15.0)) : 200.0 * m / 3.0; };
   const double mel_min = hz_to_mel(0.0), mel_max = hz_to_mel(8000.0);
@@ -25,10 +44,9 @@ void build_mel_tables(mel::Tables* t) {
   const double mel_step = (mel_max - mel_min) / (N_MELS + 1);  // numpy.linspace: arange * step + start, last = stop
   for (int i = 0; i < N_MELS + 2; ++i) ff[i] = mel_to_hz(i == N_MELS + 1 ? mel_max : i * mel_step + mel_min);
   int nnz = 0;
+  bool ok = true;
   for (int m = 0; m < N_MELS; ++m) {
-    t->fptr[m] = nnz;
-    t->flo[m] = 0;
-    bool started = false;
+    int lo = -1, cnt = 0;
     const double enorm = 2.0 / (ff[m + 2] - ff[m]);
     for (int k = 0; k < N_BINS; ++k) {
       const double f = 8000.0 * k / (N_BINS - 1);
@@ -36,148 +54,387 @@ void build_mel_tables(mel::Tables* t) {
       const double up = (ff[m + 2] - f) / (ff[m + 2] - ff[m + 1]);
       const double v = std::fmax(0.0, std::fmin(down, up)) * enorm;
       if (v > 0.0) {
-        if (!started) { t->flo[m] = k; started = true; }
-        // bins of one triangle are contiguous
+        if (lo < 0) lo = k;
+        if (k != lo + cnt) ok = false;  // bins of one triangle are contiguous
         if (nnz < MAX_NNZ) t->fw[nnz] = static_cast<float>(v);
         ++nnz;
+        ++cnt;
       }
     }
+    if (lo != kMelLo[m] || cnt != kMelCnt[m]) ok = false;
   }
-  t->fptr[N_MELS] = nnz;
+  return ok && nnz == kMelNnz;
+}
+
+cudaError_t upload_mel_constants(const mel::Tables* host_tables) {
+  return cudaMemcpyToSymbol(c_mel_fw, host_tables->fw, sizeof(float) * mel::MAX_NNZ);
 }
 
 namespace {
 
 using namespace mel;
 
+constexpr int MAX_DEFERRED_FWD = 16;
 struct MelSmem {
-  float slab[SLAB];
-  float2 X[FB * NC];
-  float2 Y[FB * NC];   // reused as the power buffer [FB][P_PITCH] (FB*P_PITCH floats <= 2*FB*NC)
-  float2 w400[N_FFT];
-  float window[N_FFT];
-  int fptr[N_MELS + 1];
-  int flo[N_MELS];
-  float fw[MAX_NNZ];
+  float slab[SLAB_ROWS * SLAB_PITCH];   // 23.9 KB  [hop row][160 (+ alignment shift)]
+  float2 E[FB * K1 * E_PITCH];          // 59.9 KB  [frame * 13 + k1][16 j (+2 pad)]
+  float P[FB * P_PITCH];                // 26.8 KB  [frame][bin]
+  Item desc[2];                         // current / next work item (the next one arrives by cp.async)
+  Item deferred[MAX_DEFERRED_FWD];          // clamp items whose clip was not finished when their ticket came up
+  int idx[2];
+  int n_deferred;
+  int run_clamp;                        // broadcast: 0 = nothing to do, 1 = clamp sm.clamp with sm.floor_v
+  Item clamp;
   float red[THREADS / 32];
+  float floor_v;
+  unsigned long long mbar;              // completion of the bulk copies of a slab
 };
-static_assert(FB * P_PITCH <= 2 * FB * NC, "power buffer must fit in Y");
+constexpr int MAX_DEFERRED = MAX_DEFERRED_FWD;
+static_assert(sizeof(Item) == 48, "Item is copied as three 16-byte cp.async transfers");
+static_assert((SLAB_ROWS - 1) * SLAB_PITCH + ROW_COPY <= SLAB_ROWS * SLAB_PITCH, "bulk row copies stay inside the slab");
 
-template <int R>
-__device__ __forceinline__ void fft_stage(const float2* X, float2* Y, const float2* w400, int s, int m, int tw_step, int nf) {
-  const int per_frame = m * s;  // butterflies per frame
-  for (int item = threadIdx.x; item < nf * per_frame; item += THREADS) {
-    const int f = item / per_frame, it = item - f * per_frame;
-    butterfly<R>(X + f * NC, Y + f * NC, w400, it, s, m, tw_step);
+// ---- mel phase: filters [M, MEnd) for the lane's frame, fully unrolled from the compiled-in structure --------------
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int M, int MEnd>
+struct MelRun {
+  static __device__ __forceinline__ void run(const float* __restrict__ prow, float* __restrict__ optr, long long ld, bool live, float& vmax) {
+    constexpr int cnt = kMelCnt[M], ptr = kMelPtr[M], lo = kMelLo[M];
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < cnt; ++j) acc = fmaf(c_mel_fw[ptr + j], prow[lo + j], acc);
+    const float v = lg2_fast(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;  // log10
+    if (live) *optr = v;
+    vmax = fmaxf(vmax, v);
+    MelRun<M + 1, MEnd>::run(prow, optr + ld, ld, live, vmax);
   }
-  __syncthreads();
+};
+template <int MEnd>
+struct MelRun<MEnd, MEnd> {
+  static __device__ __forceinline__ void run(const float*, float*, long long, bool, float&) {}
+};
+template <int G>
+__device__ __forceinline__ void mel_group(const float* __restrict__ prow, float* __restrict__ ocol, long long ld, bool live, float& vmax) {
+  constexpr int m0 = kMelGroup[G], m1 = kMelGroup[G + 1];
+  MelRun<m0, m1>::run(prow, ocol + m0 * ld, ld, live, vmax);
 }
 
-__global__ void __launch_bounds__(THREADS) logmel_kernel(const float* __restrict__ pcm, const MelSlab* __restrict__ slabs,
-                                                         const Tables* __restrict__ tables, float* __restrict__ out,
-                                                         long long ld, unsigned int* __restrict__ clip_max) {
-  extern __shared__ uint8_t smem_raw[];
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+// clip-relative sample index of slab position 0
+__device__ __forceinline__ int slab_s0(const Item& it) { return it.frame0 * HOP - N_FFT / 2; }
+
+// One thread: start the bulk copies of an item's slab (34 hop rows of 164 floats from the 16-byte aligned address at or
+// below the row's first sample; stage 1 adds the 0..3 float shift back).
+__device__ __forceinline__ void issue_slab_bulk(MelSmem& sm, const float* __restrict__ pcm, const Item& it) {
+  const float* src = pcm + it.pcm_off + slab_s0(it);
+  src -= (reinterpret_cast<uintptr_t>(src) >> 2) & 3;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the slab vs the async writes
+  mbar_expect_tx(&sm.mbar, SLAB_ROWS * ROW_COPY * 4);
+#pragma unroll 1
+  for (int r = 0; r < SLAB_ROWS; ++r) bulk_g2s(sm.slab + r * SLAB_PITCH, src + r * HOP, ROW_COPY * 4, &sm.mbar);
+}
+
+__global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restrict__ pcm, const Item* __restrict__ items, int n_items,
+                                                            const Tables* __restrict__ tables, float* __restrict__ out, long long ld,
+                                                            unsigned int* __restrict__ ticket, unsigned int* __restrict__ clip_done,
+                                                            unsigned int* __restrict__ clip_max) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   MelSmem& sm = *reinterpret_cast<MelSmem*>(smem_raw);
-  const MelSlab sl = slabs[blockIdx.x];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // constants -> smem
-  for (int i = tid; i < N_FFT; i += THREADS) { sm.w400[i] = tables->w400[i]; sm.window[i] = tables->window[i]; }
-  for (int i = tid; i < N_MELS + 1; i += THREADS) sm.fptr[i] = tables->fptr[i];
-  for (int i = tid; i < N_MELS; i += THREADS) sm.flo[i] = tables->flo[i];
-  for (int i = tid; i < MAX_NNZ; i += THREADS) sm.fw[i] = tables->fw[i];
+  // per-thread constants, loaded once for all items
+  const int j = tid & 15;                 // stage 1: sample phase j of frame (tid >> 4) [+16]
+  float win[25];
+#pragma unroll
+  for (int m = 0; m < 25; ++m) win[m] = __ldg(tables->window + 16 * m + j);
+  const int k1 = tid % K1;                // stage 2: output family k1 of frame (tid / 13) [+16], threads 0..207
+  float2 tw[16];
+#pragma unroll
+  for (int jj = 1; jj < 16; ++jj) tw[jj] = __ldg(&tables->tw[k1][jj]);
 
-  // PCM slab with centred reflect padding resolved by index mirroring
-  const float* clip = pcm + sl.pcm_off;
-  const int s0 = sl.frame0 * HOP - N_FFT / 2;
-  const int need = (sl.n_frames - 1) * HOP + N_FFT;
-  for (int u = tid; u < SLAB; u += THREADS) {
-    float v = 0.f;
-    if (u < need) v = __ldg(clip + reflect_index(s0 + u, sl.n_samples));
-    sm.slab[u] = v;
-  }
-  __syncthreads();
-
-  // window + pack: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1]
-  const int nf = sl.n_frames;
-  for (int item = tid; item < nf * NC; item += THREADS) {
-    const int f = item / NC, n = item - f * NC;
-    const float* x = sm.slab + f * HOP + 2 * n;
-    sm.X[item] = make_float2(x[0] * sm.window[2 * n], x[1] * sm.window[2 * n + 1]);
-  }
-  __syncthreads();
-
-  // 200-point complex FFT, Stockham autosort, radices 5,5,4,2 (n = 200, 40, 8, 2)
-  fft_stage<5>(sm.X, sm.Y, sm.w400, 1, 40, 2, nf);
-  fft_stage<5>(sm.Y, sm.X, sm.w400, 5, 8, 10, nf);
-  fft_stage<4>(sm.X, sm.Y, sm.w400, 25, 2, 50, nf);
-  fft_stage<2>(sm.Y, sm.X, sm.w400, 100, 1, 200, nf);
-
-  // power spectrum of the real DFT -> Y (as floats)
-  float* P = reinterpret_cast<float*>(sm.Y);
-  for (int item = tid; item < nf * N_BINS; item += THREADS) {
-    const int f = item / N_BINS, k = item - f * N_BINS;
-    P[f * P_PITCH + k] = power_bin(sm.X + f * NC, sm.w400, k);
-  }
-  __syncthreads();
-
-  // sparse mel + log10; item = (filter m, frame f) with f fastest so a filter row writes FB contiguous floats
-  float vmax = -INFINITY;
-  float* orow = out + sl.col0 + sl.frame0;
-  for (int item = tid; item < N_MELS * FB; item += THREADS) {
-    const int m = item / FB, f = item - m * FB;
-    if (f < nf) {
-      const int b = sm.fptr[m], e = sm.fptr[m + 1];
-      const float* p = P + f * P_PITCH + sm.flo[m];
-      float acc = 0.f;
-      for (int j = b; j < e; ++j) acc = fmaf(sm.fw[j], p[j - b], acc);
-      const float v = log10f(fmaxf(acc, 1e-10f));
-      vmax = fmaxf(vmax, v);
-      orow[m * ld + f] = v;
+  // Work distribution: thread 0 keeps two tickets ahead (t_next: descriptor being fetched, t_after: atomic in flight), so
+  // neither the atomic nor the descriptor load nor the PCM copy of the next item is ever waited for.
+  int t_next = 0, t_after = 0;
+  if (tid == 0) {
+    mbar_init(&sm.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int t0 = static_cast<int>(atomicAdd(ticket, 1u));
+    t_next = static_cast<int>(atomicAdd(ticket, 1u));
+    sm.idx[0] = t0;
+    sm.n_deferred = 0;
+    sm.run_clamp = 0;
+    if (t0 < n_items) {
+      sm.desc[0] = items[t0];
+      if (sm.desc[0].kind == 0 && sm.desc[0].bulk) issue_slab_bulk(sm, pcm, sm.desc[0]);
     }
   }
-  vmax = warp_max(vmax);
-  if ((tid & 31) == 0) sm.red[tid >> 5] = vmax;
   __syncthreads();
-  if (tid == 0) {
-    float v = sm.red[0];
-#pragma unroll
-    for (int i = 1; i < THREADS / 32; ++i) v = fmaxf(v, sm.red[i]);
-    atomicMax(clip_max + sl.clip, float_to_ordered(v));
-  }
-}
+  int slot = 0;
+  uint32_t parity = 0;
 
-// clamp to (clip max - 8) and rescale, in place.  grid = (column tiles, clips)
-__global__ void logmel_finish_kernel(float* __restrict__ out, long long ld, const long long* __restrict__ clip_cols,
-                                     const unsigned int* __restrict__ clip_max) {
-  const int clip = blockIdx.y;
-  const long long c0 = clip_cols[clip], c1 = clip_cols[clip + 1];
-  const float floor_v = ordered_to_float(clip_max[clip]) - 8.0f;
-  const long long t = c1 - c0;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < t * N_MELS;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / t, c = i - m * t;
-    float* p = out + m * ld + c0 + c;
-    *p = (fmaxf(*p, floor_v) + 4.0f) * 0.25f;
+  // clamp + rescale one tile of a finished clip, in place (the tile is still L2-resident); all threads
+  auto clamp_tile = [&](const Item& c, float floor_v) {
+    if (tid < c.n_frames) {
+      float* p = out + c.col0 + c.frame0 + tid;
+      // 16 loads in flight per thread before the first store: the compiler cannot hoist a load above a store to `out`
+#pragma unroll 1
+      for (int m0 = 0; m0 < N_MELS; m0 += 16, p += 16 * ld) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __ldcg(p + i * ld);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) __stcg(p + i * ld, (fmaxf(v[i], floor_v) + 4.0f) * 0.25f);
+      }
+    }
+  };
+  // thread 0: is the clip of clamp item c finished?  (acquire: its log-mel stores and max are then visible)
+  auto clamp_ready = [&](const Item& c) { return ld_acquire_u32(clip_done + c.clip) >= static_cast<unsigned int>(c.need); };
+  auto clamp_floor = [&](const Item& c) { return ordered_to_float(ld_acquire_u32(clip_max + c.clip)) - 8.0f; };
+
+  for (;;) {
+    const int idx = sm.idx[slot];
+    if (idx >= n_items) break;
+    const Item it = sm.desc[slot];
+    if (tid == 0) {
+      t_after = static_cast<int>(atomicAdd(ticket, 1u));
+      sm.idx[slot ^ 1] = t_next;
+      if (t_next < n_items) {
+        const char* src = reinterpret_cast<const char*>(items + t_next);
+        char* dst = reinterpret_cast<char*>(&sm.desc[slot ^ 1]);
+        cp_async16(dst, src);
+        cp_async16(dst + 16, src + 16);
+        cp_async16(dst + 32, src + 32);
+      }
+    }
+
+    if (it.kind == 1) {
+      // ---------------- clamp item: run it if its clip is finished, otherwise set it aside (never block) ----------------
+      if (tid == 0) {
+        if (sm.n_deferred == MAX_DEFERRED) {  // (practically never) no room to defer: wait for the oldest deferred one
+          while (!clamp_ready(sm.deferred[0])) __nanosleep(100);
+        }
+        if (sm.n_deferred > 0 && clamp_ready(sm.deferred[0])) {
+          // keep FIFO order: run the oldest deferred item now and queue this one behind the rest
+          sm.clamp = sm.deferred[0];
+          for (int i = 1; i < sm.n_deferred; ++i) sm.deferred[i - 1] = sm.deferred[i];
+          sm.deferred[sm.n_deferred - 1] = it;
+          sm.floor_v = clamp_floor(sm.clamp);
+          sm.run_clamp = 1;
+        } else if (sm.n_deferred == 0 && clamp_ready(it)) {
+          sm.clamp = it;
+          sm.floor_v = clamp_floor(it);
+          sm.run_clamp = 1;
+        } else {
+          sm.deferred[sm.n_deferred++] = it;
+          sm.run_clamp = 0;
+        }
+        // the slab is idle during a clamp item: start the next item's copy right away
+        cp_async_wait_all();
+        if (t_next < n_items && sm.desc[slot ^ 1].kind == 0 && sm.desc[slot ^ 1].bulk) issue_slab_bulk(sm, pcm, sm.desc[slot ^ 1]);
+        t_next = t_after;
+      }
+      __syncthreads();
+      if (sm.run_clamp) clamp_tile(sm.clamp, sm.floor_v);
+      __syncthreads();  // sm.clamp / floor_v / descriptor slots are rewritten by later iterations
+      slot ^= 1;
+      continue;
+    }
+
+    // ---------------- PCM slab in smem ----------------
+    int shift = 0;
+    if (it.bulk) {
+      shift = static_cast<int>((reinterpret_cast<uintptr_t>(pcm + it.pcm_off + slab_s0(it)) >> 2) & 3);
+      mbar_wait(&sm.mbar, parity);
+      parity ^= 1;
+    } else {
+      // clip edges: reflect padding resolved by index mirroring; positions no valid frame touches are zero.
+      // Loads are issued in batches of 11 before their stores so that their latencies overlap.
+      const float* clip = pcm + it.pcm_off;
+      const int s0 = slab_s0(it);
+      const int need = (it.n_frames - 1) * HOP + N_FFT;
+#pragma unroll 1
+      for (int base = 0; base < 22; base += 11) {
+        float v[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+          const int u = tid + (base + i) * THREADS;
+          v[i] = u < need ? __ldg(clip + reflect_index(s0 + u, it.n_samples)) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+          const int u = tid + (base + i) * THREADS;
+          if (u < SLAB_ROWS * HOP) {
+            const int r = u / HOP;
+            sm.slab[r * SLAB_PITCH + (u - r * HOP)] = v[i];
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---------------- stage 1: 16 real 25-point DFTs per frame ----------------
+#pragma unroll 1
+    for (int rnd = 0; rnd < 2; ++rnd) {
+      const int f = (tid >> 4) + 16 * rnd;
+      const float* x = sm.slab + shift + f * SLAB_PITCH + j;
+      float v[25];
+#pragma unroll
+      for (int m = 0; m < 25; ++m) v[m] = x[(m / 10) * SLAB_PITCH + 16 * (m % 10)] * win[m];
+      float2 V[K1];
+      rdft25(v, V);
+      float2* e = sm.E + f * K1 * E_PITCH + j;
+#pragma unroll
+      for (int q = 0; q < K1; ++q) e[q * E_PITCH] = V[q];
+    }
+    __syncthreads();  // E complete, slab free
+
+    if (tid == 0) {
+      cp_async_wait_all();
+      if (t_next < n_items && sm.desc[slot ^ 1].kind == 0 && sm.desc[slot ^ 1].bulk) issue_slab_bulk(sm, pcm, sm.desc[slot ^ 1]);
+      t_next = t_after;
+    }
+
+    // ---------------- stage 2: 13 complex 16-point FFTs per frame -> power ----------------
+    if (tid < 16 * K1) {
+#pragma unroll 1
+      for (int rnd = 0; rnd < 2; ++rnd) {
+        const int row = tid + 16 * K1 * rnd;      // = frame * 13 + k1
+        const int f = row / K1;
+        const float4* e = reinterpret_cast<const float4*>(sm.E + row * E_PITCH);
+        float2 z[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 q = e[c];
+          z[2 * c] = make_float2(q.x, q.y);
+          z[2 * c + 1] = make_float2(q.z, q.w);
+        }
+#pragma unroll
+        for (int jj = 1; jj < 16; ++jj) z[jj] = cmul(z[jj], tw[jj]);
+        fft16(z);
+        float* prow = sm.P + f * P_PITCH;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float pw = fmaf(z[k2].x, z[k2].x, z[k2].y * z[k2].y);
+          if (stage2_unique(k1, k2)) prow[stage2_bin(k1, k2)] = pw;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- mel + log10: warp = filter group, lane = frame ----------------
+    {
+      const bool live = lane < it.n_frames;
+      const float* prow = sm.P + lane * P_PITCH;
+      float* ocol = out + it.col0 + it.frame0 + lane;
+      float vmax = -INFINITY;
+      switch (warp) {
+        case 0: mel_group<0>(prow, ocol, ld, live, vmax); break;
+        case 1: mel_group<1>(prow, ocol, ld, live, vmax); break;
+        case 2: mel_group<2>(prow, ocol, ld, live, vmax); break;
+        case 3: mel_group<3>(prow, ocol, ld, live, vmax); break;
+        case 4: mel_group<4>(prow, ocol, ld, live, vmax); break;
+        case 5: mel_group<5>(prow, ocol, ld, live, vmax); break;
+        case 6: mel_group<6>(prow, ocol, ld, live, vmax); break;
+        default: mel_group<7>(prow, ocol, ld, live, vmax); break;
+      }
+      vmax = warp_max(live ? vmax : -INFINITY);
+      if (lane == 0) sm.red[warp] = vmax;
+    }
+    const int n_def = sm.n_deferred;  // read before the barrier: thread 0 only changes it after one, so every thread agrees
+    __syncthreads();
+    if (tid == 0) {
+      float v = sm.red[0];
+#pragma unroll
+      for (int i = 1; i < THREADS / 32; ++i) v = fmaxf(v, sm.red[i]);
+      // the barrier ordered every thread's log-mel stores before this point; the fence makes them (and the max) visible
+      // device-wide before the clip's done counter moves
+      atomicMax(clip_max + it.clip, float_to_ordered(v));
+      __threadfence();
+      atomicAdd(clip_done + it.clip, 1u);
+    }
+    if (n_def > 0) {
+      // a clamp item is waiting: run the oldest one if its clip has finished meanwhile
+      if (tid == 0) {
+        sm.run_clamp = 0;
+        if (clamp_ready(sm.deferred[0])) {
+          sm.clamp = sm.deferred[0];
+          for (int i = 1; i < sm.n_deferred; ++i) sm.deferred[i - 1] = sm.deferred[i];
+          --sm.n_deferred;
+          sm.floor_v = clamp_floor(sm.clamp);
+          sm.run_clamp = 1;
+        }
+      }
+      __syncthreads();
+      if (sm.run_clamp) clamp_tile(sm.clamp, sm.floor_v);
+      __syncthreads();
+    }
+    slot ^= 1;
+  }
+
+  // no tickets left: every frame item is running or finished, so the remaining deferred clamps can simply be waited for
+  for (;;) {
+    __syncthreads();
+    if (sm.n_deferred == 0) break;
+    if (tid == 0) {
+      sm.clamp = sm.deferred[sm.n_deferred - 1];
+      while (!clamp_ready(sm.clamp)) __nanosleep(100);
+      sm.floor_v = clamp_floor(sm.clamp);
+    }
+    __syncthreads();
+    clamp_tile(sm.clamp, sm.floor_v);
+    __syncthreads();
+    if (tid == 0) --sm.n_deferred;
   }
 }
 
 }  // namespace
 
-cudaError_t launch_logmel(const float* pcm, const MelSlab* slabs, int n_slabs, const mel::Tables* tables, float* mel_out,
-                          long long mel_ld, unsigned int* clip_max, cudaStream_t stream) {
-  if (n_slabs == 0) return cudaSuccess;
+cudaError_t launch_logmel(const float* pcm, const mel::Item* items, int n_items, const mel::Tables* tables, float* mel_out,
+                          long long mel_ld, unsigned int* counters, int n_clips, int num_sms, cudaStream_t stream) {
+  if (n_items == 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MelSmem)));
   if (e != cudaSuccess) return e;
-  logmel_kernel<<<n_slabs, mel::THREADS, sizeof(MelSmem), stream>>>(pcm, slabs, tables, mel_out, mel_ld, clip_max);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_logmel_finish(float* mel_out, long long mel_ld, const long long* clip_cols, int n_clips,
-                                 const unsigned int* clip_max, cudaStream_t stream) {
-  if (n_clips == 0) return cudaSuccess;
-  dim3 grid(64, n_clips);
-  logmel_finish_kernel<<<grid, 256, 0, stream>>>(mel_out, mel_ld, clip_cols, clip_max);
+  // counters: [0] ticket, [1, 1 + n_clips) done, [1 + n_clips, 1 + 2 n_clips) max (ordered-uint encoding; 0 = below every float)
+  e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (1 + 2 * static_cast<size_t>(n_clips)), stream);
+  if (e != cudaSuccess) return e;
+  const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  logmel_kernel<<<grid, mel::THREADS, sizeof(MelSmem), stream>>>(pcm, items, n_items, tables, mel_out, mel_ld, counters, counters + 1,
+                                                                 counters + 1 + n_clips);
   return cudaGetLastError();
 }
 

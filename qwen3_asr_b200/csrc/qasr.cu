@@ -455,9 +455,14 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->keep_debug = e != nullptr && e[0] == '1';
 
   mel::Tables* host_tables = new mel::Tables();
-  build_mel_tables(host_tables);
-  int rc = dev_alloc(h, reinterpret_cast<void**>(&h->mel_tables), sizeof(mel::Tables));
-  if (rc == 0 && cudaMemcpy(h->mel_tables, host_tables, sizeof(mel::Tables), cudaMemcpyHostToDevice) != cudaSuccess) {
+  int rc = 0;
+  if (!build_mel_tables(host_tables)) {
+    set_last_error("the computed mel filter bank does not match the compiled-in structure (mel_structure.inc)");
+    rc = 2;
+  }
+  if (rc == 0) rc = dev_alloc(h, reinterpret_cast<void**>(&h->mel_tables), sizeof(mel::Tables));
+  if (rc == 0 && (cudaMemcpy(h->mel_tables, host_tables, sizeof(mel::Tables), cudaMemcpyHostToDevice) != cudaSuccess ||
+                  upload_mel_constants(host_tables) != cudaSuccess)) {
     set_last_error("uploading the mel tables failed");
     rc = 2;
   }
@@ -632,7 +637,7 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
 
   long long cols = 0;
-  size_t n_slabs = 0;
+  size_t n_items = 0;
   for (int i = 0; i < n_clips; ++i) {
     const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
     QASR_REQUIRE(n > mel::N_FFT / 2, "qasr_logmel: every clip needs more than 200 samples (reflect padding), clip " + std::to_string(i) +
@@ -641,46 +646,59 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
     const int64_t t = n / mel::HOP;
     if (feature_lens_out != nullptr) feature_lens_out[i] = t;
     cols += t;
-    n_slabs += static_cast<size_t>((t + mel::FB - 1) / mel::FB);
+    n_items += static_cast<size_t>((t + mel::FB - 1) / mel::FB) + static_cast<size_t>((t + mel::CLAMP_TILE - 1) / mel::CLAMP_TILE);
   }
   QASR_REQUIRE(mel_ld >= cols, "qasr_logmel: mel_ld smaller than the total frame count");
   if (cols == 0) return 0;
 
-  const size_t o_slab = 0;
-  const size_t o_cols = align_up(n_slabs * sizeof(MelSlab), 16);
-  const size_t total = o_cols + (static_cast<size_t>(n_clips) + 1) * sizeof(long long);
+  // Work list in ticket order: frame items clip by clip; the clamp items of a clip are emitted once kClampLag frame
+  // items of later clips lie behind it (or at the end), so that a clamp practically never waits.  Every frame item a
+  // clamp waits for has a smaller ticket, hence is running or finished: no deadlock for any grid size.
+  const size_t total = n_items * sizeof(mel::Item);
   Staging* st = nullptr;
   if (staging_acquire(h, total, &st) != 0) return 2;
-  MelSlab* slabs = reinterpret_cast<MelSlab*>(st->host + o_slab);
-  long long* ccols = reinterpret_cast<long long*>(st->host + o_cols);
-  size_t si = 0;
+  mel::Item* items = reinterpret_cast<mel::Item*>(st->host);
+  const int64_t buf_samples = clip_offsets[n_clips];
+  const int kClampLag = 4 * h->num_sms;
+  size_t ni = 0;
   long long col = 0;
+  struct Pending { int clip, t; long long col0; size_t emitted_at; };
+  std::vector<Pending> pending;
+  size_t frame_items = 0, pend_head = 0;
+  auto emit_clamps = [&](const Pending& p) {
+    const int need = (p.t + mel::FB - 1) / mel::FB;
+    for (int f0 = 0; f0 < p.t; f0 += mel::CLAMP_TILE) {
+      mel::Item& it = items[ni++];
+      it.kind = 1; it.clip = p.clip; it.frame0 = f0; it.n_frames = std::min(mel::CLAMP_TILE, p.t - f0);
+      it.n_samples = 0; it.need = need; it.bulk = 0; it.pad_ = 0; it.pcm_off = 0; it.col0 = p.col0;
+    }
+  };
   for (int i = 0; i < n_clips; ++i) {
     const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
     const int t = static_cast<int>(n / mel::HOP);
-    ccols[i] = col;
     for (int f0 = 0; f0 < t; f0 += mel::FB) {
-      MelSlab& s = slabs[si++];
-      s.clip = i;
-      s.frame0 = f0;
-      s.n_frames = std::min(mel::FB, t - f0);
-      s.n_samples = static_cast<int>(n);
-      s.pcm_off = clip_offsets[i];
-      s.col0 = col;
+      mel::Item& it = items[ni++];
+      it.kind = 0; it.clip = i; it.frame0 = f0; it.n_frames = std::min(mel::FB, t - f0);
+      it.n_samples = static_cast<int>(n); it.need = 0; it.pad_ = 0; it.pcm_off = clip_offsets[i]; it.col0 = col;
+      // bulk path: no reflection for the valid frames and all 34 row copies (164 floats each) inside the PCM buffer
+      const int64_t s0 = static_cast<int64_t>(f0) * mel::HOP - mel::N_FFT / 2;
+      const int64_t need = static_cast<int64_t>(it.n_frames - 1) * mel::HOP + mel::N_FFT;
+      it.bulk = (s0 >= 0 && s0 + need <= n &&
+                 clip_offsets[i] + s0 + static_cast<int64_t>(mel::SLAB_ROWS - 1) * mel::HOP + mel::ROW_COPY <= buf_samples) ? 1 : 0;
+      ++frame_items;
+      while (pend_head < pending.size() && frame_items - pending[pend_head].emitted_at >= static_cast<size_t>(kClampLag))
+        emit_clamps(pending[pend_head++]);
     }
+    if (t > 0) pending.push_back({i, t, col, frame_items});
     col += t;
   }
-  ccols[n_clips] = col;
+  while (pend_head < pending.size()) emit_clamps(pending[pend_head++]);
   QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
-  if (grow(h, &h->clipmax_buf, static_cast<size_t>(n_clips) * sizeof(unsigned int)) != 0) return 2;
-  unsigned int* cmax = static_cast<unsigned int*>(h->clipmax_buf.p);
-  QASR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, static_cast<size_t>(n_clips) * sizeof(unsigned int), stream));
+  if (grow(h, &h->clipmax_buf, (2 * static_cast<size_t>(n_clips) + 1) * sizeof(unsigned int)) != 0) return 2;
   const double mel_bytes = 4.0 * static_cast<double>(clip_offsets[n_clips] - clip_offsets[0]) + 4.0 * mel::N_MELS * static_cast<double>(cols);
   QASR_LAUNCH(h, "logmel", mel_bytes, stream,
-              launch_logmel(pcm_dev, reinterpret_cast<const MelSlab*>(st->dev + o_slab), static_cast<int>(n_slabs), h->mel_tables,
-                            mel_out_dev, mel_ld, cmax, stream));
-  QASR_LAUNCH(h, "logmel_finish", 0, stream,
-              launch_logmel_finish(mel_out_dev, mel_ld, reinterpret_cast<const long long*>(st->dev + o_cols), n_clips, cmax, stream));
+              launch_logmel(pcm_dev, reinterpret_cast<const mel::Item*>(st->dev), static_cast<int>(ni), h->mel_tables, mel_out_dev, mel_ld,
+                            static_cast<unsigned int*>(h->clipmax_buf.p), n_clips, h->num_sms, stream));
   QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
   st->in_flight = true;
   h->last_mel_cols = cols;
