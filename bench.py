@@ -233,7 +233,24 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     step_dev = lambda: enc.encode_pcm_packed(pcm_dev, offs, out_dev)
-    step_e2e = lambda: enc.encode_pcm_host(pcm_host, offs, out_host)
+    out_host2 = torch.empty_like(out_host).pin_memory()
+    pending = []
+
+    def step_e2e():
+        # the serving loop: batch i+1 is submitted (H2D copy + compute enqueued) before batch i's result is awaited, so the
+        # copies of one batch overlap the compute of its neighbours; every step still moves its own input and output
+        buf = out_host if step_e2e.n % 2 == 0 else out_host2
+        step_e2e.n += 1
+        t, _ = enc.submit_pcm_host(pcm_host, offs, buf)
+        pending.append(t)
+        if len(pending) > 1:
+            enc.wait(pending.pop(0))
+
+    step_e2e.n = 0
+
+    def drain_e2e():
+        while pending:
+            enc.wait(pending.pop(0))
 
     for _ in range(args.warmup):
         step_dev()
@@ -250,7 +267,23 @@ def main():
 
     for _ in range(2):
         step_e2e()
-    ms_e2e, win_e2e = timed(step_e2e, args.steps)
+    drain_e2e()
+
+    # timed region = K submits + the final drain (all K results on the host), events on the compute stream + wall clock
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    drain_e2e()
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms_e2e, win_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0)), (w0, w1)
+    ms_e2e_wall = max_over_ranks((w1 - w0) * 1e3)
+    ms_e2e = max(ms_e2e, ms_e2e_wall)  # the D2H copies run on a side stream: the wall clock bounds them too
+    enc.encode_pcm_host(pcm_host, offs, out_host)  # leave the reference output of this batch in out_host for the CPU check
 
     # mel kernel alone on a working set >> L2 (8 x the C2 batch: 491 MB PCM in, 393 MB log-mel out)
     mel_prof = None
@@ -320,7 +353,8 @@ def main():
             "dtype": "bf16", "data": "synthetic", "config": workload_config(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pcm_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 2),
-                    "api": "qasr_encode_pcm_host (C ABI, pinned host buffers, sync per step)"},
+                    "api": "qasr_submit_pcm_host + qasr_wait (C ABI, pinned host buffers; batch i+1 submitted before batch i is awaited; "
+                           "time = max(device events, host wall clock) over K submits and the final drain)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline, "roofline_mel": roofline_mel, "kernels": kernels,

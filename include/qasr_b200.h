@@ -122,6 +122,15 @@ QASR_API int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_
 QASR_API int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                          int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream);
 
+/* Pipelined form of qasr_encode_pcm_host for back-to-back batches (the serving loop): returns as soon as the
+ * work is enqueued -- host->device copy on an internal copy stream, log-mel + encoder on `stream`, device->host copy
+ * on a second internal stream -- so that the copies of one batch overlap the compute of its neighbours (device
+ * buffers are double-buffered).  qasr_wait(ticket) blocks until out_host holds that batch.  pcm_host and out_host
+ * must stay valid (and should be pinned) until then.  At most two submits may be un-waited at any time. */
+QASR_API int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream, uint64_t* ticket_out);
+QASR_API int qasr_wait(qasr_handle_t h, uint64_t ticket);
+
 /* Log-mel end to end with host buffers (float32 [128, sum T] out). */
 QASR_API int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
                      int64_t* feature_lens_out, void* stream);

@@ -46,6 +46,8 @@ SIGNATURES = {
     "qasr_encode": (C.c_int, [_P, _P, C.c_int, C.c_int64, _I64P, C.c_int, _P, _I64P, _P]),
     "qasr_encode_pcm": (C.c_int, [_P, _P, _I64P, C.c_int, _P, _I64P, _P]),
     "qasr_encode_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P]),
+    "qasr_submit_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P, C.POINTER(C.c_uint64)]),
+    "qasr_wait": (C.c_int, [_P, C.c_uint64]),
     "qasr_logmel_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, _I64P, _P]),
     "qasr_destroy": (None, [_P]),
     "qasr_launch_count": (C.c_uint64, [_P]),

@@ -124,6 +124,15 @@ struct qasr_handle_s {
   int next_slot = 0;
   GrowBuf mel_buf, pcm_buf, out_buf, clipmax_buf;
 
+  // double-buffered host <-> device pipeline of qasr_submit_pcm_host / qasr_wait
+  struct Pipe {
+    GrowBuf pcm, out;
+    cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
+    uint64_t seq = 0;  // ticket of the submit that last used this slot (0 = never)
+  } pipe[2];
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  uint64_t next_ticket = 1;
+
   // launch accounting + optional per-launch CUDA-event timing (qasr_profile_*)
   unsigned long long launches = 0;
   bool profiling = false;
@@ -804,12 +813,13 @@ int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_o
   return qasr_encode(h, mel, QASR_F32, ld, flens.data(), n_clips, out_dev, token_lens_out, stream);
 }
 
-int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
-                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream_v) {
-  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_encode_pcm_host: bad argument");
-  QASR_REQUIRE(h->finalized, "qasr_encode_pcm_host before qasr_finalize");
+int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream_v, uint64_t* ticket_out) {
+  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0 && ticket_out != nullptr, "qasr_submit_pcm_host: bad argument");
+  QASR_REQUIRE(h->finalized, "qasr_submit_pcm_host before qasr_finalize");
+  *ticket_out = 0;
   if (n_clips == 0) return 0;
-  QASR_REQUIRE(pcm_host != nullptr && out_host != nullptr, "qasr_encode_pcm_host: null buffer");
+  QASR_REQUIRE(pcm_host != nullptr && out_host != nullptr, "qasr_submit_pcm_host: null buffer");
   DeviceGuard guard(h->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int64_t base = clip_offsets[0];
@@ -818,16 +828,59 @@ int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* 
   std::vector<int64_t> offs(n_clips + 1);
   for (int i = 0; i <= n_clips; ++i) offs[i] = clip_offsets[i] - base;
   for (int i = 0; i < n_clips; ++i) tokens += qasr_token_len((offs[i + 1] - offs[i]) / mel::HOP);
-  QASR_REQUIRE(tokens <= out_capacity_tokens, "qasr_encode_pcm_host: output buffer too small for " + std::to_string(tokens) + " tokens");
-  if (grow(h, &h->pcm_buf, static_cast<size_t>(n_samples) * sizeof(float)) != 0) return 2;
+  QASR_REQUIRE(tokens <= out_capacity_tokens, "qasr_submit_pcm_host: output buffer too small for " + std::to_string(tokens) + " tokens");
+
+  if (h->s_in == nullptr) {
+    QASR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    QASR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (auto& pp : h->pipe) {
+      QASR_CUDA_CHECK(cudaEventCreateWithFlags(&pp.ev_in, cudaEventDisableTiming));
+      QASR_CUDA_CHECK(cudaEventCreateWithFlags(&pp.ev_comp, cudaEventDisableTiming));
+      QASR_CUDA_CHECK(cudaEventCreateWithFlags(&pp.ev_out, cudaEventDisableTiming));
+    }
+  }
+  const uint64_t ticket = h->next_ticket++;
+  qasr_handle_s::Pipe& pp = h->pipe[ticket & 1];
   const size_t out_bytes = static_cast<size_t>(tokens) * h->cfg.output_dim * sizeof(bf16);
-  if (grow(h, &h->out_buf, out_bytes) != 0) return 2;
-  QASR_CUDA_CHECK(cudaMemcpyAsync(h->pcm_buf.p, pcm_host + base, static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, stream));
-  const int rc = qasr_encode_pcm(h, static_cast<const float*>(h->pcm_buf.p), offs.data(), n_clips, h->out_buf.p, token_lens_out, stream);
+  if (grow(h, &pp.pcm, static_cast<size_t>(n_samples) * sizeof(float)) != 0) return 2;   // growing synchronises the device
+  if (grow(h, &pp.out, out_bytes) != 0) return 2;
+  // the slot's previous user (ticket - 2): its compute must have finished reading pp.pcm before the copy engine overwrites
+  // it, its device->host copy must have drained pp.out before this compute overwrites it
+  if (pp.seq != 0) {
+    QASR_CUDA_CHECK(cudaStreamWaitEvent(h->s_in, pp.ev_comp, 0));
+    QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, pp.ev_out, 0));
+  }
+  QASR_CUDA_CHECK(cudaMemcpyAsync(pp.pcm.p, pcm_host + base, static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+  QASR_CUDA_CHECK(cudaEventRecord(pp.ev_in, h->s_in));
+  QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, pp.ev_in, 0));
+  const int rc = qasr_encode_pcm(h, static_cast<const float*>(pp.pcm.p), offs.data(), n_clips, pp.out.p, token_lens_out, stream);
   if (rc != 0) return rc;
-  if (out_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(out_host, h->out_buf.p, out_bytes, cudaMemcpyDeviceToHost, stream));
-  QASR_CUDA_CHECK(cudaStreamSynchronize(stream));
+  QASR_CUDA_CHECK(cudaEventRecord(pp.ev_comp, stream));
+  QASR_CUDA_CHECK(cudaStreamWaitEvent(h->s_out, pp.ev_comp, 0));
+  if (out_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(out_host, pp.out.p, out_bytes, cudaMemcpyDeviceToHost, h->s_out));
+  QASR_CUDA_CHECK(cudaEventRecord(pp.ev_out, h->s_out));
+  pp.seq = ticket;
+  *ticket_out = ticket;
   return 0;
+}
+
+int qasr_wait(qasr_handle_t h, uint64_t ticket) {
+  QASR_REQUIRE(h != nullptr, "qasr_wait: null handle");
+  if (ticket == 0) return 0;
+  QASR_REQUIRE(ticket < h->next_ticket, "qasr_wait: unknown ticket");
+  DeviceGuard guard(h->device);
+  qasr_handle_s::Pipe& pp = h->pipe[ticket & 1];
+  // a later submit on the same slot waited for this ticket's copies on the device; its own event then covers both
+  if (pp.seq != 0) QASR_CUDA_CHECK(cudaEventSynchronize(pp.ev_out));
+  return 0;
+}
+
+int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream_v) {
+  uint64_t ticket = 0;
+  const int rc = qasr_submit_pcm_host(h, pcm_host, clip_offsets, n_clips, out_host, out_capacity_tokens, token_lens_out, stream_v, &ticket);
+  if (rc != 0) return rc;
+  return qasr_wait(h, ticket);
 }
 
 int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
@@ -867,8 +920,13 @@ void qasr_destroy(qasr_handle_t h) {
   }
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
-  for (GrowBuf* b : {&h->mel_buf, &h->pcm_buf, &h->out_buf, &h->clipmax_buf})
+  for (GrowBuf* b : {&h->mel_buf, &h->pcm_buf, &h->out_buf, &h->clipmax_buf, &h->pipe[0].pcm, &h->pipe[0].out, &h->pipe[1].pcm, &h->pipe[1].out})
     if (b->p != nullptr) cudaFree(b->p);
+  for (auto& pp : h->pipe)
+    for (cudaEvent_t e : {pp.ev_in, pp.ev_comp, pp.ev_out})
+      if (e != nullptr) cudaEventDestroy(e);
+  if (h->s_in != nullptr) cudaStreamDestroy(h->s_in);
+  if (h->s_out != nullptr) cudaStreamDestroy(h->s_out);
   delete h;
 }
 

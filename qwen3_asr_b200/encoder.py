@@ -218,6 +218,24 @@ class B200AudioEncoder:
               "qasr_encode_pcm_host")
         return toks
 
+    def submit_pcm_host(self, pcm_host: torch.Tensor, offsets: np.ndarray, out_host: torch.Tensor):
+        """Pipelined end-to-end call: enqueue H2D + log-mel + encoder + D2H and return (ticket, token_lens) at once;
+        ``wait(ticket)`` blocks until ``out_host`` is filled.  Keep at most two tickets un-waited."""
+        assert not pcm_host.is_cuda and pcm_host.dtype == torch.float32 and pcm_host.is_contiguous()
+        assert not out_host.is_cuda and out_host.dtype == torch.bfloat16 and out_host.is_contiguous()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        toks = np.zeros(n, dtype=np.int64)
+        ticket = C.c_uint64(0)
+        check(self.lib, self.lib.qasr_submit_pcm_host(self._h, C.c_void_p(pcm_host.data_ptr()), offsets.ctypes.data_as(_lib._I64P), n,
+                                                      C.c_void_p(out_host.data_ptr()), int(out_host.shape[0]),
+                                                      toks.ctypes.data_as(_lib._I64P), self._stream(), C.byref(ticket)),
+              "qasr_submit_pcm_host")
+        return int(ticket.value), toks
+
+    def wait(self, ticket: int) -> None:
+        check(self.lib, self.lib.qasr_wait(self._h, C.c_uint64(int(ticket))), "qasr_wait")
+
     def logmel_host(self, clips: Sequence[np.ndarray]):
         offs = np.zeros(len(clips) + 1, dtype=np.int64)
         for i, c in enumerate(clips):

@@ -261,6 +261,37 @@ def test_encoder_microbatch_split_is_exact(tiny):
         small.close()
 
 
+def test_pipelined_submit_wait_matches_synchronous_call(tiny):
+    """qasr_submit_pcm_host / qasr_wait (double-buffered copies overlapping compute) return the same bits as the
+    synchronous host entry point, for several different batches in flight back to back."""
+    from oracle.signals import speech_like
+
+    _, _, enc = tiny
+    batches = []
+    for b in range(5):
+        clips = [speech_like(t * 160 + 13 * b, 900 + 10 * b + i) for i, t in enumerate((333 + 50 * b, 77, 1056))]
+        offs = np.zeros(len(clips) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([c.shape[0] for c in clips])
+        pcm = torch.from_numpy(np.concatenate(clips)).pin_memory()
+        n_tok = sum(enc.token_len(c.shape[0] // 160) for c in clips)
+        batches.append((pcm, offs, n_tok))
+    ref = []
+    for pcm, offs, n_tok in batches:
+        out = torch.empty((n_tok, enc.output_dim), dtype=torch.bfloat16).pin_memory()
+        enc.encode_pcm_host(pcm, offs, out)
+        ref.append(out.clone())
+    outs = [torch.zeros((n_tok, enc.output_dim), dtype=torch.bfloat16).pin_memory() for _, _, n_tok in batches]
+    tickets = []
+    for (pcm, offs, _), out in zip(batches, outs):
+        t, _ = enc.submit_pcm_host(pcm, offs, out)
+        tickets.append(t)
+        if len(tickets) > 1:
+            enc.wait(tickets[-2])
+    enc.wait(tickets[-1])
+    for a, b in zip(ref, outs):
+        assert torch.equal(a, b)
+
+
 def test_forward_signature_matches_audio_tower(tiny):
     """forward(input_features[128, sum T], feature_lens) -> .last_hidden_state, and the hook's [1,128,T] form."""
     from oracle import logmel
