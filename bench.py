@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quantize", default=None, choices=["fp8", "fp8_per_row"],
+                    help="BASELINE.json configs[4](i): e4m3 Linears with dynamic activation scales (the reference's QUANTIZE=fp8); default bf16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -193,7 +195,7 @@ def main():
     peaks = load_peaks()
     cfg = model_config(MODEL)
     weights = random_weights(cfg, seed=0)
-    enc = B200AudioEncoder(cfg, weights, device=local_rank)
+    enc = B200AudioEncoder(cfg, weights, device=local_rank, quantize=args.quantize)
     n = int(CLIP_SECONDS * SR)
     clips = [speech_like(n, rank * N_CLIPS + i) for i in range(N_CLIPS)]
     audio_s_per_step = N_CLIPS * CLIP_SECONDS
@@ -350,7 +352,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": workload_config(),
+            "dtype": "bf16" if args.quantize is None else f"e4m3 Linears ({args.quantize}) + bf16 convs/attention", "data": "synthetic",
+            "config": workload_config(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pcm_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 2),
                     "api": "qasr_submit_pcm_host + qasr_wait (C ABI, pinned host buffers; batch i+1 submitted before batch i is awaited; "

@@ -42,6 +42,14 @@ extern "C" {
 
 typedef struct qasr_handle_s* qasr_handle_t;
 
+/* qasr_config_t.flags.  QASR_FLAG_FP8 mirrors the reference's QUANTIZE=fp8 (src/server.py:362-371: torchao
+ * Float8DynamicActivationFloat8WeightConfig on every nn.Linear, convolutions untouched): e4m3 weights, activations
+ * quantised dynamically before every Linear, fp32 accumulate, bf16 out.  Default granularity is per-tensor (one scale
+ * per weight module and per activation tensor of the call); QASR_FLAG_FP8_PER_ROW switches to per-output-channel weight
+ * scales and per-token activation scales (torchao's PerRow), which is invariant to how clips are batched. */
+#define QASR_FLAG_FP8 1
+#define QASR_FLAG_FP8_PER_ROW 2
+
 /* dtypes for qasr_set_weight / qasr_encode */
 #define QASR_F32 0
 #define QASR_BF16 1
@@ -64,7 +72,7 @@ typedef struct qasr_config_s {
    * 0 = defaults (1024 chunks = 1024 audio-seconds, 13312 tokens) */
   int32_t max_chunks;
   int32_t max_tokens;
-  int32_t flags;                /* reserved, must be 0 */
+  int32_t flags;                /* QASR_FLAG_* bits, 0 = bf16 */
 } qasr_config_t;
 
 QASR_API int qasr_abi_version(void);
@@ -157,6 +165,11 @@ QASR_API int qasr_debug_read(qasr_handle_t h, const char* name, void* dst_host, 
  * bias float32 or NULL; act: 0 none, 1 GELU. */
 QASR_API int qasr_debug_gemm(const void* a, const void* b, const float* bias, const void* residual, void* d, int m, int n, int k, int act,
                     int impl, void* stream);
+/* bf16 [rows, k] -> e4m3 [rows, k] + row_scale[rows] (per_row = 0: one tensor-wide scale replicated); synchronises. */
+QASR_API int qasr_debug_quant_fp8(const void* x, int rows, int k, void* q_out, float* row_scale_out, int per_row, void* stream);
+/* D[M,N] = act(A8[M,K] * B8[N,K]^T * row_scale[m] * col_scale[n] + bias) (+ residual), e4m3 operands, bf16 out. */
+QASR_API int qasr_debug_gemm_fp8(const void* a8, const void* b8, const float* row_scale, const float* col_scale, const float* bias,
+                        const void* residual, void* d, int m, int n, int k, int act, void* stream);
 QASR_API int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int d, void* stream);
 QASR_API int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream);
 

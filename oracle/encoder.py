@@ -171,6 +171,38 @@ def _rnd(x: torch.Tensor, emulate_bf16: bool) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32) if emulate_bf16 else x
 
 
+E4M3_MAX = 448.0
+AMAX_EPS = 1e-12
+
+
+def _e4m3(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """x / scale rounded to float8_e4m3fn (round-to-nearest-even, saturating), returned as float32."""
+    return (x / scale).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn).to(torch.float32)
+
+
+def linear_fp8(x: torch.Tensor, weight: torch.Tensor, bias, mode: str) -> torch.Tensor:
+    """nn.Linear under torchao's Float8DynamicActivationFloat8WeightConfig (reference src/server.py:362-371), emulated:
+    e4m3 weight and dynamically quantised e4m3 activation, fp32 accumulate, y = (xq @ wq^T) * sx * sw + bias.
+    ``mode``: "per_tensor" (one scale per tensor) or "per_row" (per token / per output channel).  torchao itself is
+    not installable offline: this restates its documented recipe (scale = max(amax, 1e-12) / 448) -- PARITY UNPINNED."""
+    x = x.float()
+    w = weight.float()
+    if mode == "per_row":
+        sx = x.abs().amax(dim=1, keepdim=True).clamp(min=AMAX_EPS) / E4M3_MAX
+        sw = w.abs().amax(dim=1, keepdim=True).clamp(min=AMAX_EPS) / E4M3_MAX
+    elif mode == "per_tensor":
+        sx = (x.abs().amax().clamp(min=AMAX_EPS) / E4M3_MAX).reshape(1, 1)
+        sw = (w.abs().amax().clamp(min=AMAX_EPS) / E4M3_MAX).reshape(1, 1)
+    else:
+        raise ValueError(mode)
+    y = (_e4m3(x, sx) @ _e4m3(w, sw).T) * sx * sw.T
+    return y if bias is None else y + bias
+
+
+def _linear(x, weight, bias, fp8):
+    return F.linear(x, weight, bias) if fp8 is None else linear_fp8(x, weight, bias, fp8)
+
+
 def _conv_stem(w, chunks: torch.Tensor, emulate_bf16: bool) -> torch.Tensor:
     """[n, 1, 128, W] -> [n, 480, 16, W''] (:729-734), exact-erf GELU after each conv."""
     x = chunks
@@ -180,11 +212,11 @@ def _conv_stem(w, chunks: torch.Tensor, emulate_bf16: bool) -> torch.Tensor:
     return x
 
 
-def _attention(w, prefix: str, h: torch.Tensor, wins, cfg: EncoderConfig, emulate_bf16: bool) -> torch.Tensor:
+def _attention(w, prefix: str, h: torch.Tensor, wins, cfg: EncoderConfig, emulate_bf16: bool, fp8=None) -> torch.Tensor:
     hd, nh = cfg.head_dim, cfg.heads
-    q = _rnd(F.linear(h, w[prefix + "q_proj.weight"], w[prefix + "q_proj.bias"]), emulate_bf16)
-    k = _rnd(F.linear(h, w[prefix + "k_proj.weight"], w[prefix + "k_proj.bias"]), emulate_bf16)
-    v = _rnd(F.linear(h, w[prefix + "v_proj.weight"], w[prefix + "v_proj.bias"]), emulate_bf16)
+    q = _rnd(_linear(h, w[prefix + "q_proj.weight"], w[prefix + "q_proj.bias"], fp8), emulate_bf16)
+    k = _rnd(_linear(h, w[prefix + "k_proj.weight"], w[prefix + "k_proj.bias"], fp8), emulate_bf16)
+    v = _rnd(_linear(h, w[prefix + "v_proj.weight"], w[prefix + "v_proj.bias"], fp8), emulate_bf16)
     out = torch.empty_like(q)
     s = 0
     scale = hd ** -0.5
@@ -197,15 +229,20 @@ def _attention(w, prefix: str, h: torch.Tensor, wins, cfg: EncoderConfig, emulat
         out[s : s + wl] = (att @ vs).transpose(0, 1).reshape(wl, nh * hd)
         s += wl
     out = _rnd(out, emulate_bf16)
-    return _rnd(F.linear(out, w[prefix + "out_proj.weight"], w[prefix + "out_proj.bias"]), emulate_bf16)
+    return _rnd(_linear(out, w[prefix + "out_proj.weight"], w[prefix + "out_proj.bias"], fp8), emulate_bf16)
 
 
 @torch.no_grad()
-def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, return_intermediate: bool = False):
+def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, return_intermediate: bool = False, fp8=None):
     """mels: list of float32 [128, T_i] (already at the precision the tower sees,
     e.g. rounded through bf16).  Returns (hidden [sum tokens, output_dim] float32,
     token_lens list).  ``emulate_bf16`` rounds every module output through bf16,
-    the reference deployment's rounding points."""
+    the reference deployment's rounding points.
+    ``fp8``: None, "per_tensor" or "per_row" -- every nn.Linear (conv_out, q/k/v/out_proj, fc1, fc2, proj1, proj2)
+    through ``linear_fp8``; the convolutions stay as they are (torchao's default filter).
+    Per-tensor activation scales are taken over the whole call, as torchao takes them over the tensor it is handed."""
+    if fp8 is not None:
+        emulate_bf16 = True
     mels = [torch.as_tensor(np.asarray(m), dtype=torch.float32) for m in mels]
     cf = cfg.chunk_frames
     d = cfg.d_model
@@ -238,14 +275,24 @@ def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, ret
         for (ci, slot, valid), y in zip(full_owner, ys):
             per_clip_tokens[ci][slot] = (y, valid)
 
-    rows, token_lens = [], []
+    # conv_out is ONE nn.Linear call over every chunk's time steps (:735-737) -- for the fp8 per-tensor variant its
+    # dynamic activation scale therefore spans all of them, padded tail positions included
+    emb_in, emb_meta = [], []
     for toks in per_clip_tokens:
-        n_tok = 0
         for (y, valid) in toks:
             c, f, tw = y.shape
-            emb = y.permute(2, 0, 1).reshape(tw, c * f)  # index c*16+f (:735-736)
-            emb = _rnd(F.linear(emb, w["conv_out.weight"]), emulate_bf16)
-            emb = _rnd(emb + pe[:tw], emulate_bf16)  # positions restart per chunk (:738-743)
+            emb_in.append(y.permute(2, 0, 1).reshape(tw, c * f))  # index c*16+f (:735-736)
+            emb_meta.append((tw, valid))
+    emb_all = _rnd(_linear(torch.cat(emb_in, dim=0), w["conv_out.weight"], None, fp8), emulate_bf16) if emb_in else torch.zeros(0, d)
+    rows, token_lens = [], []
+    pos, mi = 0, 0
+    for toks in per_clip_tokens:
+        n_tok = 0
+        for _ in toks:
+            tw, valid = emb_meta[mi]
+            mi += 1
+            emb = _rnd(emb_all[pos : pos + tw] + pe[:tw], emulate_bf16)  # positions restart per chunk (:738-743)
+            pos += tw
             nv = token_len(valid)
             rows.append(emb[:nv])
             n_tok += nv
@@ -260,19 +307,19 @@ def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, ret
     for li in range(cfg.layers):
         p = f"layers.{li}."
         h = _rnd(F.layer_norm(x, (d,), w[p + "self_attn_layer_norm.weight"], w[p + "self_attn_layer_norm.bias"], 1e-5), emulate_bf16)
-        x = _rnd(x + _attention(w, p + "self_attn.", h, wins, cfg, emulate_bf16), emulate_bf16)
+        x = _rnd(x + _attention(w, p + "self_attn.", h, wins, cfg, emulate_bf16, fp8), emulate_bf16)
         h = _rnd(F.layer_norm(x, (d,), w[p + "final_layer_norm.weight"], w[p + "final_layer_norm.bias"], 1e-5), emulate_bf16)
-        h = _rnd(F.linear(h, w[p + "fc1.weight"], w[p + "fc1.bias"]), emulate_bf16)
+        h = _rnd(_linear(h, w[p + "fc1.weight"], w[p + "fc1.bias"], fp8), emulate_bf16)
         h = _rnd(F.gelu(h), emulate_bf16)
-        h = _rnd(F.linear(h, w[p + "fc2.weight"], w[p + "fc2.bias"]), emulate_bf16)
+        h = _rnd(_linear(h, w[p + "fc2.weight"], w[p + "fc2.bias"], fp8), emulate_bf16)
         x = _rnd(x + h, emulate_bf16)
         if return_intermediate and li == 0:
             inter["layer0"] = x.clone()
 
     x = _rnd(F.layer_norm(x, (d,), w["ln_post.weight"], w["ln_post.bias"], 1e-5), emulate_bf16)
-    x = _rnd(F.linear(x, w["proj1.weight"], w["proj1.bias"]), emulate_bf16)
+    x = _rnd(_linear(x, w["proj1.weight"], w["proj1.bias"], fp8), emulate_bf16)
     x = _rnd(F.gelu(x), emulate_bf16)
-    x = _rnd(F.linear(x, w["proj2.weight"], w["proj2.bias"]), emulate_bf16)
+    x = _rnd(_linear(x, w["proj2.weight"], w["proj2.bias"], fp8), emulate_bf16)
     if return_intermediate:
         return x, token_lens, inter
     return x, token_lens

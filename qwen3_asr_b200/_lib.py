@@ -56,6 +56,8 @@ SIGNATURES = {
                                     C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)]),
     "qasr_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qasr_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "qasr_debug_quant_fp8": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "qasr_debug_gemm_fp8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "qasr_debug_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "qasr_debug_attention": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, _P]),
 }

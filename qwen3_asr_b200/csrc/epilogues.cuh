@@ -69,6 +69,7 @@ struct EpiLinear {
   long long ldo;
   int m_valid, n_valid;
   struct Prefetch { uint4 r; };
+  static constexpr bool kScaled = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return n_valid; }
   __device__ __forceinline__ bool row_live(int) const { return true; }
@@ -93,6 +94,18 @@ struct EpiLinear {
   }
 };
 
+// FP8 (e4m3 x e4m3) variants: the fp32 accumulator is first dequantised with the dynamic activation scale of its row
+// and the weight scale of its column -- y = acc * sa[m] * sw[n] + bias, what torch._scaled_mm computes for torchao's
+// Float8DynamicActivationFloat8WeightConfig (reference src/server.py:362-371) -- then follows the bf16 epilogue unchanged.
+template <class Base>
+struct Scaled : Base {
+  const float* row_scale_p;   // [M] activation scales (per-tensor mode: all equal)
+  const float* col_scale_p;   // [N] weight scales (per-tensor mode: equal within a module)
+  static constexpr bool kScaled = true;
+  __device__ __forceinline__ const float* col_scale_ptr() const { return col_scale_p; }
+  __device__ __forceinline__ float row_scale(int m) const { return m < this->m_valid ? __ldg(row_scale_p + m) : 0.f; }
+};
+
 // Implicit-GEMM convolution epilogue: row m = (global output column g, output row h) with
 // g = chunk * slots + ow.  Writes bf16(gelu(bf16(acc + bias))) into the next layer's
 // [column][row][channel] layout at column chunk * out_pitch + out_off + ow; columns at or beyond
@@ -108,6 +121,7 @@ struct EpiConv {
   int out_pitch, out_off;  // destination column = chunk * out_pitch + out_off + ow
   int n_chunks, c;         // c = channels (480)
   typedef NoPrefetch Prefetch;
+  static constexpr bool kScaled = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return c; }
   __device__ __forceinline__ bool row_live(int m) const {
@@ -139,6 +153,7 @@ struct EpiConvOut {
   int tok_per_chunk;       // 13
   int d, m_valid;
   struct Prefetch { float4 a, b; };
+  static constexpr bool kScaled = false;
   __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
   __device__ __forceinline__ int n_cols() const { return d; }
   __device__ __forceinline__ bool row_live(int) const { return true; }

@@ -48,6 +48,23 @@ int make_tmap_rowmajor(CUtensorMap* tm, const void* base, long long rows, long l
   return 0;
 }
 
+int make_tmap_rowmajor_u8(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  if (tmap_api_init() != 0) return 2;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(tc::BLOCK_K_BYTES), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(2d, u8) failed with CUresult " + std::to_string(static_cast<int>(r)) + " rows=" +
+                   std::to_string(rows) + " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld));
+    return 2;
+  }
+  return 0;
+}
+
 int make_tmap_conv(CUtensorMap* tm, const void* base, long long g_in, int h_in, int c, int hc, int gt) {
   if (tmap_api_init() != 0) return 2;
   const cuuint64_t dims[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(h_in), static_cast<cuuint64_t>(g_in)};
@@ -74,12 +91,12 @@ int pick_bn(int n) {
 
 namespace {
 
-template <int BN, int AMODE, class Epi>
+template <int BN, int AMODE, int KIND, class Epi>
 cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc::GemmShape& shape, const Epi& epi, int num_sms,
                       cudaStream_t stream) {
   constexpr int ST = tc::default_stages<BN>();
-  using L = tc::SmemLayout<BN, ST>;
-  auto kern = tc::gemm_tc_kernel<BN, ST, AMODE, Epi>;
+  using L = tc::SmemLayout<BN, ST, Epi::kScaled>;
+  auto kern = tc::gemm_tc_kernel<BN, ST, AMODE, KIND, Epi>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
   if (e != cudaSuccess) return e;
   const int tiles = shape.m_tiles * shape.n_tiles;
@@ -99,44 +116,48 @@ cudaError_t launch_simt(const ALoad& aload, const __nv_bfloat16* b, long long ld
   return cudaGetLastError();
 }
 
-template <class Epi>
+template <int KIND, class Epi>
 cudaError_t linear_dispatch(const LinearArgs& a, const Epi& epi, bool simt, int num_sms, cudaStream_t stream) {
   if (simt) {
+    if (KIND != tc::K_BF16) return cudaErrorNotSupported;  // the SIMT checker reads bf16 operands
     tc::ALoadLinear al{a.a, a.lda, a.m};
     return launch_simt(al, a.b, a.ldb, a.m, a.n, a.k, epi, stream);
   }
   tc::GemmShape sh{};
   sh.m_tiles = (a.m + tc::BLOCK_M - 1) / tc::BLOCK_M;
   sh.n_tiles = a.n / a.bn;
-  sh.num_kb = a.k / tc::BLOCK_K;
+  sh.num_kb = a.k / tc::block_k_elems<KIND>();
   sh.kb_per_tap = 1;
   sh.gt = 1;
   switch (a.bn) {
-    case 256: return launch_tc<256, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
-    case 128: return launch_tc<128, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
-    case 64: return launch_tc<64, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
+    case 256: return launch_tc<256, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
+    case 128: return launch_tc<128, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
+    case 64: return launch_tc<64, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+template <int ACT, bool RES>
+cudaError_t linear_kind(const LinearArgs& a, const __nv_bfloat16* residual, bool simt, int num_sms, cudaStream_t stream) {
+  EpiLinear<ACT, RES> e{a.out, a.bias, residual, a.ldo, a.m, a.n};
+  if (a.fp8) {
+    Scaled<EpiLinear<ACT, RES>> se{e, a.row_scale, a.col_scale};
+    return linear_dispatch<tc::K_E4M3>(a, se, simt, num_sms, stream);
+  }
+  return linear_dispatch<tc::K_BF16>(a, e, simt, num_sms, stream);
 }
 
 }  // namespace
 
 cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_t stream) {
   if (a.m <= 0) return cudaSuccess;
-  if (a.k % tc::BLOCK_K != 0 || a.n % 16 != 0 || (!simt && (a.bn == 0 || a.n % a.bn != 0))) return cudaErrorInvalidValue;
+  const int kb = a.fp8 ? tc::block_k_elems<tc::K_E4M3>() : tc::BLOCK_K;
+  if (a.k % kb != 0 || a.n % 16 != 0 || (!simt && (a.bn == 0 || a.n % a.bn != 0))) return cudaErrorInvalidValue;
+  if (a.fp8 && (a.row_scale == nullptr || a.col_scale == nullptr)) return cudaErrorInvalidValue;
   switch (a.epi) {
-    case LIN_PLAIN: {
-      EpiLinear<ACT_NONE, false> e{a.out, a.bias, nullptr, a.ldo, a.m, a.n};
-      return linear_dispatch(a, e, simt, num_sms, stream);
-    }
-    case LIN_GELU: {
-      EpiLinear<ACT_GELU, false> e{a.out, a.bias, nullptr, a.ldo, a.m, a.n};
-      return linear_dispatch(a, e, simt, num_sms, stream);
-    }
-    case LIN_RESIDUAL: {
-      EpiLinear<ACT_NONE, true> e{a.out, a.bias, a.residual, a.ldo, a.m, a.n};
-      return linear_dispatch(a, e, simt, num_sms, stream);
-    }
+    case LIN_PLAIN: return linear_kind<ACT_NONE, false>(a, nullptr, simt, num_sms, stream);
+    case LIN_GELU: return linear_kind<ACT_GELU, false>(a, nullptr, simt, num_sms, stream);
+    case LIN_RESIDUAL: return linear_kind<ACT_NONE, true>(a, a.residual, simt, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -156,29 +177,43 @@ cudaError_t gemm_conv(const ConvArgs& a, bool simt, int num_sms, cudaStream_t st
   sh.num_kb = 9 * 8;
   sh.kb_per_tap = 8;
   sh.gt = a.gt;
-  return launch_tc<240, tc::A_CONV>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+  return launch_tc<240, tc::A_CONV, tc::K_BF16>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
 }
 
-cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStream_t stream) {
-  if (a.m <= 0) return cudaSuccess;
-  if (a.k % tc::BLOCK_K != 0 || a.d % 16 != 0) return cudaErrorInvalidValue;
-  EpiConvOut e{a.out, a.pe, a.row_token, a.tok_per_chunk, a.d, a.m};
-  if (simt) {
-    tc::ALoadLinear al{a.a, a.k, a.m};
-    return launch_simt(al, a.b, a.k, a.m, a.d, a.k, e, stream);
-  }
+namespace {
+template <int KIND, class Epi>
+cudaError_t conv_out_dispatch(const ConvOutArgs& a, const Epi& e, int num_sms, cudaStream_t stream) {
   tc::GemmShape sh{};
   sh.m_tiles = (a.m + tc::BLOCK_M - 1) / tc::BLOCK_M;
   sh.n_tiles = a.d / a.bn;
-  sh.num_kb = a.k / tc::BLOCK_K;
+  sh.num_kb = a.k / tc::block_k_elems<KIND>();
   sh.kb_per_tap = 1;
   sh.gt = 1;
   switch (a.bn) {
-    case 256: return launch_tc<256, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
-    case 128: return launch_tc<128, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
-    case 64: return launch_tc<64, tc::A_LINEAR>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+    case 256: return launch_tc<256, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+    case 128: return launch_tc<128, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
+    case 64: return launch_tc<64, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, e, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+}  // namespace
+
+cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStream_t stream) {
+  if (a.m <= 0) return cudaSuccess;
+  const int kb = a.fp8 ? tc::block_k_elems<tc::K_E4M3>() : tc::BLOCK_K;
+  if (a.k % kb != 0 || a.d % 16 != 0) return cudaErrorInvalidValue;
+  EpiConvOut e{a.out, a.pe, a.row_token, a.tok_per_chunk, a.d, a.m};
+  if (simt) {
+    if (a.fp8) return cudaErrorNotSupported;
+    tc::ALoadLinear al{a.a, a.k, a.m};
+    return launch_simt(al, a.b, a.k, a.m, a.d, a.k, e, stream);
+  }
+  if (a.fp8) {
+    if (a.row_scale == nullptr || a.col_scale == nullptr) return cudaErrorInvalidValue;
+    Scaled<EpiConvOut> se{e, a.row_scale, a.col_scale};
+    return conv_out_dispatch<tc::K_E4M3>(a, se, num_sms, stream);
+  }
+  return conv_out_dispatch<tc::K_BF16>(a, e, num_sms, stream);
 }
 
 }  // namespace qasr

@@ -13,6 +13,8 @@ int tmap_api_init();
 
 // bf16 row-major [rows, cols] (leading dimension ld elements), box = box_rows x 64 columns, 128B swizzle.
 int make_tmap_rowmajor(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// e4m3 (one byte per element) row-major [rows, cols], box = box_rows x 128 columns, 128B swizzle.
+int make_tmap_rowmajor_u8(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows);
 // bf16 activation [g_in columns][h_in rows][c channels] read by a 3x3 stride-2 convolution as
 // implicit GEMM: box = 64 channels x hc output rows x gt output columns, traversal stride 2 on
 // rows and columns.
@@ -37,6 +39,11 @@ struct LinearArgs {
   long long ldo;
   const float* bias;           // [n] or nullptr
   const __nv_bfloat16* residual;  // LIN_RESIDUAL: [m, ldo]
+  // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,
+  // y = acc * row_scale[m] * col_scale[n] + bias
+  int fp8;
+  const float* row_scale;      // [m]
+  const float* col_scale;      // [n]
 };
 cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_t stream);
 
@@ -71,6 +78,9 @@ struct ConvOutArgs {
   const int* row_token;        // [m]
   int tok_per_chunk;
   __nv_bfloat16* out;          // [tokens, d]
+  int fp8;                     // as in LinearArgs
+  const float* row_scale;
+  const float* col_scale;
 };
 cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStream_t stream);
 

@@ -32,6 +32,13 @@ cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, con
                          const float* w /*[C][9]*/, const float* bias /*[C]*/, int channels,
                          __nv_bfloat16* act1, cudaStream_t stream);
 
+// ---- FP8 dynamic quantisation (quant.cu) -----------------------------------------------------
+// x: bf16 [rows, k] (ld ldx) -> q: e4m3 [rows, k] (ld ldq bytes) + row_scale[rows].  per_row = false: one scale for
+// the whole tensor (amax_slot: a zeroed uint32 on the device), written to every row_scale entry.
+cudaError_t launch_quant_fp8(const __nv_bfloat16* x, long long ldx, int rows, int k, uint8_t* q, long long ldq, float* row_scale,
+                             unsigned int* amax_slot, bool per_row, int num_sms, cudaStream_t stream);
+void quantize_weight_e4m3(const float* w, int n, int k, int modules, bool per_row, uint8_t* q_out, float* scale_out);
+
 // ---- LayerNorm -------------------------------------------------------------------------------
 cudaError_t launch_layernorm(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* out,
                              int rows, int d, float eps, cudaStream_t stream);

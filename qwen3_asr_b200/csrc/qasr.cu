@@ -48,10 +48,12 @@ struct HostTensor {
 };
 
 struct LinearW {
-  bf16* w = nullptr;    // [n, k]
-  float* b = nullptr;   // [n] or nullptr
+  bf16* w = nullptr;       // [n, k] (bf16 mode)
+  uint8_t* w8 = nullptr;   // [n, k] e4m3 (fp8 mode)
+  float* wscale = nullptr; // [n] weight scales (fp8 mode)
+  float* b = nullptr;      // [n] or nullptr
   int n = 0, k = 0, bn = 0;
-  CUtensorMap tm;
+  CUtensorMap tm;          // over w or w8
 };
 
 struct LayerW {
@@ -95,6 +97,8 @@ struct qasr_handle_s {
   int device = 0;
   int num_sms = kNumSMs;
   bool finalized = false;
+  bool fp8 = false;         // QASR_FLAG_FP8: e4m3 x e4m3 Linears with dynamic activation scales (QUANTIZE=fp8)
+  bool fp8_per_row = false; // QASR_FLAG_FP8_PER_ROW: per-row activation / per-output-channel weight scales (else per-tensor)
   bool simt = false;        // QASR_DEBUG_SIMT=1: run every GEMM through the SIMT checker kernel
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
   int chunks_per_window = 8;
@@ -120,6 +124,12 @@ struct qasr_handle_s {
   bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr;
   bf16 *x = nullptr, *hbuf = nullptr, *qkv = nullptr, *att = nullptr, *ffn = nullptr, *embed_dbg = nullptr;
   CUtensorMap tm_act1, tm_act2, tm_act3, tm_h, tm_att, tm_ffn;
+  // fp8 mode: the quantised copy of whichever activation feeds the next Linear, its row scales, per-call amax slots
+  uint8_t* a8 = nullptr;
+  float* a_scale = nullptr;
+  unsigned int* amax_slots = nullptr;
+  int n_amax_slots = 0;
+  CUtensorMap tm_a8_conv, tm_a8_d, tm_a8_ffn;
   Staging staging[kStagingSlots];
   int next_slot = 0;
   GrowBuf mel_buf, pcm_buf, out_buf, clipmax_buf;
@@ -263,15 +273,29 @@ int upload_bf16(qasr_handle_s* h, const float* src, size_t n, bf16** dst) {
   return 0;
 }
 
-// nn.Linear [n, k] (+ bias) -> device bf16 weight, f32 bias, TMA map with box rows = bn
-int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, LinearW* out) {
+// nn.Linear [n, k] (+ bias) -> device weight (bf16, or e4m3 + scales in fp8 mode), f32 bias, TMA map with box rows = bn.
+// `modules`: number of nn.Linear modules stacked along n (3 for the fused q|k|v weight): each owns its per-tensor scale.
+int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, LinearW* out, int modules = 1) {
   out->n = n;
   out->k = k;
   out->bn = pick_bn(n);
   QASR_REQUIRE(out->bn != 0, "linear output width " + std::to_string(n) + " is not a multiple of 64");
   QASR_REQUIRE(k % 64 == 0, "linear input width " + std::to_string(k) + " is not a multiple of 64");
-  if (upload_bf16(h, w, static_cast<size_t>(n) * k, &out->w) != 0) return 2;
   if (b != nullptr && upload_f32(h, b, n, &out->b) != 0) return 2;
+  if (h->fp8) {
+    QASR_REQUIRE(k % 128 == 0, "fp8 mode needs linear input widths that are multiples of 128, got " + std::to_string(k));
+    const size_t nk = static_cast<size_t>(n) * k;
+    std::vector<float> wb(nk);
+    for (size_t i = 0; i < nk; ++i) wb[i] = __bfloat162float(__float2bfloat16_rn(w[i]));  // the reference quantises its bf16 weights
+    std::vector<uint8_t> q(nk);
+    std::vector<float> sc(n);
+    quantize_weight_e4m3(wb.data(), n, k, modules, h->fp8_per_row, q.data(), sc.data());
+    if (dev_alloc(h, reinterpret_cast<void**>(&out->w8), nk) != 0) return 2;
+    QASR_CUDA_CHECK(cudaMemcpy(out->w8, q.data(), nk, cudaMemcpyHostToDevice));
+    if (upload_f32(h, sc.data(), n, &out->wscale) != 0) return 2;
+    return make_tmap_rowmajor_u8(&out->tm, out->w8, n, k, k, out->bn);
+  }
+  if (upload_bf16(h, w, static_cast<size_t>(n) * k, &out->w) != 0) return 2;
   return make_tmap_rowmajor(&out->tm, out->w, n, k, k, out->bn);
 }
 
@@ -372,40 +396,59 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     a.width = d_w3; a.bias = h->conv3_b; a.out = h->act3; a.c = kConvC;
     QASR_LAUNCH(h, "conv3_gemm", px3 * kConvC * 2.0 * 9 * kConvC, stream, gemm_conv(a, h->simt, h->num_sms, stream));
   }
+  // fp8 mode: every Linear input is quantised (dynamic scale) into h->a8 right before its GEMM
+  int amax_next = 0;
+  if (h->fp8 && !h->fp8_per_row) QASR_CUDA_CHECK(cudaMemsetAsync(h->amax_slots, 0, h->n_amax_slots * sizeof(unsigned int), stream));
+  auto quant = [&](const bf16* src, int rows, int k) -> cudaError_t {
+    unsigned int* slot = h->fp8_per_row ? nullptr : h->amax_slots + (amax_next++ % h->n_amax_slots);
+    return launch_quant_fp8(src, k, rows, k, h->a8, k, h->a_scale, slot, h->fp8_per_row, h->num_sms, stream);
+  };
   {
     ConvOutArgs a{};
     a.tm_a = &h->tm_act3; a.tm_b = &h->conv_out.tm; a.bn = h->conv_out.bn;
     a.a = h->act3; a.b = h->conv_out.w; a.m = nc * kTokPerChunk; a.d = d; a.k = 16 * kConvC;
     a.pe = h->pe; a.row_token = d_rt; a.tok_per_chunk = kTokPerChunk; a.out = h->x;
+    if (h->fp8) {
+      QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(h->act3, nc * kTokPerChunk, 16 * kConvC));
+      a.tm_a = &h->tm_a8_conv; a.fp8 = 1; a.row_scale = h->a_scale; a.col_scale = h->conv_out.wscale;
+    }
     QASR_LAUNCH(h, "conv_out_gemm", 2.0 * ntok * 16 * kConvC * d, stream, gemm_conv_out(a, h->simt, h->num_sms, stream));
   }
   if (h->keep_debug && h->embed_dbg != nullptr)
     QASR_CUDA_CHECK(cudaMemcpyAsync(h->embed_dbg, h->x, static_cast<size_t>(ntok) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
 
   // ---- transformer layers
-  auto linear = [&](const CUtensorMap* tm_a, const bf16* a_raw, const LinearW& w, int epi, bf16* o, long long ldo,
-                    const bf16* residual) -> cudaError_t {
+  // one nn.Linear: (fp8: quantise the bf16 input first) GEMM with fused bias / GELU / residual epilogue
+  auto linear = [&](const char* name, double flops, const CUtensorMap* tm_a, const bf16* a_raw, const LinearW& w, int epi, bf16* o,
+                    long long ldo, const bf16* residual) -> int {
     LinearArgs la{};
     la.tm_a = tm_a; la.tm_b = &w.tm; la.bn = w.bn; la.a = a_raw; la.lda = w.k; la.b = w.w; la.ldb = w.k;
     la.m = ntok; la.n = w.n; la.k = w.k; la.epi = epi; la.out = o; la.ldo = ldo; la.bias = w.b; la.residual = residual;
-    return gemm_linear(la, h->simt, h->num_sms, stream);
+    if (h->fp8) {
+      QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(a_raw, ntok, w.k));
+      la.tm_a = w.k == d ? &h->tm_a8_d : &h->tm_a8_ffn;
+      la.fp8 = 1; la.row_scale = h->a_scale; la.col_scale = w.wscale;
+    }
+    QASR_LAUNCH(h, name, flops, stream, gemm_linear(la, h->simt, h->num_sms, stream));
+    return 0;
   };
   const int n_win = static_cast<int>(mb.win.size());
+  int rc;
   for (const LayerW& L : h->layers) {
     const double tk = 2.0 * ntok;
     QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, L.ln1_g, L.ln1_b, h->hbuf, ntok, d, 1e-5f, stream));
-    QASR_LAUNCH(h, "qkv_gemm", tk * 3 * d * d, stream, linear(&h->tm_h, h->hbuf, L.qkv, LIN_PLAIN, h->qkv, 3LL * d, nullptr));
+    if ((rc = linear("qkv_gemm", tk * 3 * d * d, &h->tm_h, h->hbuf, L.qkv, LIN_PLAIN, h->qkv, 3LL * d, nullptr)) != 0) return rc;
     QASR_LAUNCH(h, "window_attention", att_flops, stream,
                 launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, stream));
-    QASR_LAUNCH(h, "out_proj_gemm", tk * d * d, stream, linear(&h->tm_att, h->att, L.out, LIN_RESIDUAL, h->x, d, h->x));
+    if ((rc = linear("out_proj_gemm", tk * d * d, &h->tm_att, h->att, L.out, LIN_RESIDUAL, h->x, d, h->x)) != 0) return rc;
     QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, L.ln2_g, L.ln2_b, h->hbuf, ntok, d, 1e-5f, stream));
-    QASR_LAUNCH(h, "fc1_gemm", tk * d * c.encoder_ffn_dim, stream, linear(&h->tm_h, h->hbuf, L.fc1, LIN_GELU, h->ffn, c.encoder_ffn_dim, nullptr));
-    QASR_LAUNCH(h, "fc2_gemm", tk * d * c.encoder_ffn_dim, stream, linear(&h->tm_ffn, h->ffn, L.fc2, LIN_RESIDUAL, h->x, d, h->x));
+    if ((rc = linear("fc1_gemm", tk * d * c.encoder_ffn_dim, &h->tm_h, h->hbuf, L.fc1, LIN_GELU, h->ffn, c.encoder_ffn_dim, nullptr)) != 0) return rc;
+    if ((rc = linear("fc2_gemm", tk * d * c.encoder_ffn_dim, &h->tm_ffn, h->ffn, L.fc2, LIN_RESIDUAL, h->x, d, h->x)) != 0) return rc;
   }
   // ---- output head
   QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, h->lnp_g, h->lnp_b, h->hbuf, ntok, d, 1e-5f, stream));
-  QASR_LAUNCH(h, "proj1_gemm", 2.0 * ntok * d * d, stream, linear(&h->tm_h, h->hbuf, h->proj1, LIN_GELU, h->att, d, nullptr));
-  QASR_LAUNCH(h, "proj2_gemm", 2.0 * ntok * d * c.output_dim, stream, linear(&h->tm_att, h->att, h->proj2, LIN_PLAIN, out, c.output_dim, nullptr));
+  if ((rc = linear("proj1_gemm", 2.0 * ntok * d * d, &h->tm_h, h->hbuf, h->proj1, LIN_GELU, h->att, d, nullptr)) != 0) return rc;
+  if ((rc = linear("proj2_gemm", 2.0 * ntok * d * c.output_dim, &h->tm_att, h->att, h->proj2, LIN_PLAIN, out, c.output_dim, nullptr)) != 0) return rc;
 
   QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
   st->in_flight = true;
@@ -439,7 +482,8 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   QASR_REQUIRE(cfg->encoder_attention_heads > 0 && cfg->d_model == cfg->encoder_attention_heads * 64, "head_dim must be 64");
   QASR_REQUIRE(cfg->n_window_infer >= 100 && cfg->n_window_infer % 100 == 0, "n_window_infer must be a positive multiple of 100");
   QASR_REQUIRE(cfg->encoder_layers >= 0 && cfg->encoder_ffn_dim > 0 && cfg->output_dim > 0, "bad layer dims");
-  QASR_REQUIRE(cfg->flags == 0, "flags must be 0");
+  QASR_REQUIRE((cfg->flags & ~(QASR_FLAG_FP8 | QASR_FLAG_FP8_PER_ROW)) == 0, "unknown bits in flags");
+  QASR_REQUIRE((cfg->flags & QASR_FLAG_FP8_PER_ROW) == 0 || (cfg->flags & QASR_FLAG_FP8) != 0, "QASR_FLAG_FP8_PER_ROW needs QASR_FLAG_FP8");
   int n_dev = 0;
   QASR_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
   QASR_REQUIRE(device >= 0 && device < n_dev, "no such CUDA device");
@@ -454,12 +498,19 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->chunks_per_window = cfg->n_window_infer / 100;
+  h->fp8 = (cfg->flags & QASR_FLAG_FP8) != 0;
+  h->fp8_per_row = (cfg->flags & QASR_FLAG_FP8_PER_ROW) != 0;
   h->max_chunks = cfg->max_chunks > 0 ? cfg->max_chunks : 1024;
   h->max_tokens = cfg->max_tokens > 0 ? cfg->max_tokens : h->max_chunks * kTokPerChunk;
   h->max_chunks = std::max(h->max_chunks, h->chunks_per_window);
   h->max_tokens = std::max(h->max_tokens, h->chunks_per_window * kTokPerChunk);
   const char* e = std::getenv("QASR_DEBUG_SIMT");
   h->simt = e != nullptr && e[0] == '1';
+  if (h->simt && h->fp8) {
+    set_last_error("QASR_DEBUG_SIMT=1 is not available in fp8 mode (the SIMT checker reads bf16 operands)");
+    delete h;
+    return 1;
+  }
   e = std::getenv("QASR_DEBUG_KEEP");
   h->keep_debug = e != nullptr && e[0] == '1';
 
@@ -587,7 +638,7 @@ int qasr_finalize(qasr_handle_t h) {
       std::memcpy(b.data(), bq->data.data(), sizeof(float) * d);
       std::memcpy(b.data() + d, bk->data.data(), sizeof(float) * d);
       std::memcpy(b.data() + 2 * d, bv->data.data(), sizeof(float) * d);
-      if ((rc = make_linear(h, w.data(), b.data(), 3 * d, d, &L.qkv)) != 0) return rc;
+      if ((rc = make_linear(h, w.data(), b.data(), 3 * d, d, &L.qkv, 3)) != 0) return rc;
     }
     if ((rc = load_linear(h, p + "self_attn.out_proj", d, d, true, &L.out)) != 0) return rc;
     if ((rc = load_linear(h, p + "fc1", ffn, d, true, &L.fc1)) != 0) return rc;
@@ -629,6 +680,19 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = make_tmap_rowmajor(&h->tm_h, h->hbuf, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_att, h->att, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_ffn, h->ffn, mt, ffn, ffn, 128)) != 0) return rc;
+  if (h->fp8) {
+    QASR_REQUIRE(d % 128 == 0 && ffn % 128 == 0, "fp8 mode needs d_model and encoder_ffn_dim to be multiples of 128");
+    const size_t rows_conv = align_up(mc * kTokPerChunk, 128);
+    const size_t a8_bytes = std::max(rows_conv * 16 * kConvC, mt * static_cast<size_t>(std::max(d, ffn)));
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->a8), a8_bytes)) != 0) return rc;
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->a_scale), std::max(rows_conv, mt) * sizeof(float))) != 0) return rc;
+    h->n_amax_slots = 4 * c.encoder_layers + 4;
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->amax_slots), h->n_amax_slots * sizeof(unsigned int))) != 0) return rc;
+    QASR_CUDA_CHECK(cudaMemset(h->a8, 0, a8_bytes));
+    if ((rc = make_tmap_rowmajor_u8(&h->tm_a8_conv, h->a8, static_cast<long long>(mc) * kTokPerChunk, 16 * kConvC, 16 * kConvC, 128)) != 0) return rc;
+    if ((rc = make_tmap_rowmajor_u8(&h->tm_a8_d, h->a8, mt, d, d, 128)) != 0) return rc;
+    if ((rc = make_tmap_rowmajor_u8(&h->tm_a8_ffn, h->a8, mt, ffn, ffn, 128)) != 0) return rc;
+  }
   QASR_CUDA_CHECK(cudaDeviceSynchronize());
   h->finalized = true;
   return 0;
@@ -1030,6 +1094,51 @@ int qasr_debug_gemm(const void* a, const void* b, const float* bias, const void*
   la.epi = residual != nullptr ? LIN_RESIDUAL : (act == 1 ? LIN_GELU : LIN_PLAIN);
   la.out = static_cast<bf16*>(d); la.ldo = n; la.bias = bias; la.residual = static_cast<const bf16*>(residual);
   QASR_CUDA_CHECK(gemm_linear(la, impl == 1, sms, stream));
+  return 0;
+}
+
+int qasr_debug_quant_fp8(const void* x, int rows, int k, void* q_out, float* row_scale_out, int per_row, void* stream_v) {
+  QASR_REQUIRE(x != nullptr && q_out != nullptr && row_scale_out != nullptr && rows > 0 && k > 0 && k % 8 == 0, "qasr_debug_quant_fp8: bad argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  int dev = 0, sms = kNumSMs;
+  QASR_CUDA_CHECK(cudaGetDevice(&dev));
+  QASR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  unsigned int* slot = nullptr;
+  QASR_CUDA_CHECK(cudaMalloc(&slot, sizeof(unsigned int)));
+  cudaError_t e = cudaMemsetAsync(slot, 0, sizeof(unsigned int), stream);
+  if (e == cudaSuccess)
+    e = launch_quant_fp8(static_cast<const bf16*>(x), k, rows, k, static_cast<uint8_t*>(q_out), k, row_scale_out, slot, per_row != 0, sms, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(slot);
+  if (e != cudaSuccess) {
+    set_last_error(std::string("qasr_debug_quant_fp8: ") + cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+int qasr_debug_gemm_fp8(const void* a8, const void* b8, const float* row_scale, const float* col_scale, const float* bias,
+                        const void* residual, void* d, int m, int n, int k, int act, void* stream_v) {
+  QASR_REQUIRE(a8 != nullptr && b8 != nullptr && row_scale != nullptr && col_scale != nullptr && d != nullptr && m > 0 && n > 0 && k > 0,
+               "qasr_debug_gemm_fp8: bad argument");
+  QASR_REQUIRE(k % 128 == 0, "qasr_debug_gemm_fp8: k must be a multiple of 128");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int bn = pick_bn(n);
+  QASR_REQUIRE(bn != 0, "qasr_debug_gemm_fp8: n must be a multiple of 64");
+  CUtensorMap tm_a, tm_b;
+  int rc;
+  if ((rc = make_tmap_rowmajor_u8(&tm_a, a8, m, k, k, 128)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor_u8(&tm_b, b8, n, k, k, bn)) != 0) return rc;
+  int dev = 0, sms = kNumSMs;
+  QASR_CUDA_CHECK(cudaGetDevice(&dev));
+  QASR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LinearArgs la{};
+  la.tm_a = &tm_a; la.tm_b = &tm_b; la.bn = bn;
+  la.m = m; la.n = n; la.k = k;
+  la.epi = residual != nullptr ? LIN_RESIDUAL : (act == 1 ? LIN_GELU : LIN_PLAIN);
+  la.out = static_cast<bf16*>(d); la.ldo = n; la.bias = bias; la.residual = static_cast<const bf16*>(residual);
+  la.fp8 = 1; la.row_scale = row_scale; la.col_scale = col_scale;
+  QASR_CUDA_CHECK(gemm_linear(la, false, sms, stream));
   return 0;
 }
 

@@ -27,8 +27,12 @@ namespace qasr {
 namespace tc {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int BLOCK_K = 64;  // bf16: 64 elements = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
+constexpr int BLOCK_K_BYTES = 128;  // every operand kind stages 128-byte rows; one UMMA consumes 32 of them
+enum Kind : int { K_BF16 = 0, K_E4M3 = 1 };  // kind::f16 (bf16 x bf16) / kind::f8f6f4 (e4m3 x e4m3), fp32 accumulate
+template <int KIND>
+constexpr int block_k_elems() { return KIND == K_E4M3 ? 128 : 64; }
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -135,13 +139,23 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND == K_E4M3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
@@ -165,6 +179,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
+// kind::f8f6f4 with both operands E4M3 (a_format = b_format = 0), fp32 accumulate, K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 // Shared-memory matrix descriptor for a K-major tile stored as rows of 128 bytes with SWIZZLE_128B
 // (exactly what a TMA box with inner extent 64 bf16 and CU_TENSOR_MAP_SWIZZLE_128B writes):
 //   [0,14) start>>4  [16,30) LBO>>4 (=1, unused for swizzled K-major)  [32,46) SBO>>4 (8 rows*128B = 1024)
@@ -173,13 +191,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN, int STAGES>
+// SCALED (fp8 kinds): bias and column-scale tables are single-buffered (an extra epilogue barrier per tile keeps a fast
+// warp from overwriting them) -- with 4 stages of 48 KB and 32 KB of staging there is no room for two copies of both.
+template <int BN, int STAGES, bool SCALED = false>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;               // [kEpiWarps][32 rows][128 B]
-  static constexpr int BIAS_OFFSET = STAGING_OFFSET + kEpiWarps * kStagingBytes;  // float [2][256]
-  static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * 256 * 4;
+  static constexpr int TAB_BUFS = SCALED ? 1 : 2;
+  static constexpr int BIAS_OFFSET = STAGING_OFFSET + kEpiWarps * kStagingBytes;  // float [TAB_BUFS][256]
+  static constexpr int SCALE_OFFSET = BIAS_OFFSET + TAB_BUFS * 256 * 4;           // float [256] column scales (SCALED only)
+  static constexpr int BAR_OFFSET = SCALE_OFFSET + (SCALED ? 256 * 4 : 0);
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -207,12 +229,14 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 //   offset(m, n)          element offset of 8 consecutive output columns, or -1 to skip them
 //   prefetch / finish     optional post-rounding addend (residual, positional table) and the final store
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int AMODE, class Epi>
+template <int BN, int STAGES, int AMODE, int KIND, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape, Epi epi) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, Epi::kScaled>;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(BN <= kAccStride, "an accumulator stage is kAccStride TMEM columns");
+  static_assert(KIND == K_BF16 || AMODE == A_LINEAR, "the implicit-GEMM convolutions stay bf16 (torchao quantises nn.Linear only)");
+  constexpr int KB_ELEMS = block_k_elems<KIND>();
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned stage bases
@@ -266,14 +290,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if constexpr (AMODE == A_LINEAR) {
-            tma_load_2d(sa, &tmA, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
+            tma_load_2d(sa, &tmA, kb * KB_ELEMS, m_blk * BLOCK_M, &full_bar[stage]);
           } else {
             const int kh = tap / 3, kw = tap - kh * 3;
             // input column = 2 * (global output column) + kw (left zero column is part of the layout),
             // input row    = 2 * (output row) + kh - 1    (row -1 is out of bounds -> TMA zero fill)
-            tma_load_3d(sa, &tmA, cb * BLOCK_K, kh - 1, 2 * (m_blk * shape.gt) + kw, &full_bar[stage]);
+            tma_load_3d(sa, &tmA, cb * KB_ELEMS, kh - 1, 2 * (m_blk * shape.gt) + kw, &full_bar[stage]);
           }
-          tma_load_2d(sb, &tmB, kb * BLOCK_K, n_blk * BN, &full_bar[stage]);
+          tma_load_2d(sb, &tmB, kb * KB_ELEMS, n_blk * BN, &full_bar[stage]);
         }
         __syncwarp();
         if (++cb == shape.kb_per_tap) { cb = 0; ++tap; }
@@ -283,9 +307,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // The whole warp walks the pipeline (converged waits); one elected lane issues.  Descriptor bases of the ring's
-    // stages are loop invariants; the per-k advance (16 elements = 32 bytes inside the 128B swizzle atom) is +2 in
-    // the >>4 address field.
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
+    // stages are loop invariants; the per-k advance (one UMMA = 32 bytes of K inside the 128B swizzle atom: 16 bf16 or
+    // 32 e4m3) is +2 in the >>4 address field.
+    constexpr uint32_t idesc = KIND == K_E4M3 ? make_idesc_e4m3(BLOCK_M, BN) : make_idesc_bf16(BLOCK_M, BN);
     const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem));
     int stage = 0;
     uint32_t phase = 0;
@@ -303,8 +327,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t db = da + static_cast<uint64_t>(A_STAGE_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K_BYTES / 32; ++k)
+            umma<KIND>(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == shape.num_kb - 1) umma_commit(&tmem_full_bar[as]);
         }
@@ -320,6 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - kEpiWarp0 * 32;
     const uint32_t stage_base = smem_u32(smem + L::STAGING_OFFSET + ew * kStagingBytes);
     float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+    float* scale_s = reinterpret_cast<float*>(smem + L::SCALE_OFFSET);
     constexpr int NP = (BN + kPanel - 1) / kPanel;
     const int sub = lane >> 3, ch = lane & 7;  // phase B: row within a 4-row group, 16-byte chunk of the row segment
     int iter = 0;
@@ -328,18 +353,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_blk = tile % shape.n_tiles;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
+      const int tab = as % L::TAB_BUFS;
       {  // this tile's bias columns -> smem (overlaps the tile's MMAs)
         const float* bp = epi.bias_ptr();
         const int n = n_blk * BN + et;
         float b = 0.f;
         if (et < BN && bp != nullptr && n < epi.n_cols()) b = __ldg(bp + n);
-        if (et < 256) bias_s[as * 256 + et] = b;
+        if (et < 256) bias_s[tab * 256 + et] = b;
+        if constexpr (Epi::kScaled) {
+          float cs = 0.f;
+          if (et < BN && n < epi.n_cols()) cs = __ldg(epi.col_scale_ptr() + n);
+          if (et < 256) scale_s[et] = cs;
+        }
       }
       named_bar_sync(1, kEpiThreads);
       wait_tmem_full(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const int row0 = m_blk * BLOCK_M + q * 32;
       const bool live = epi.row_live(row0 + lane);
+      float row_scale = 1.f;
+      if constexpr (Epi::kScaled) row_scale = epi.row_scale(row0 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
 #pragma unroll 1
       for (int p = half; p < NP; p += 2) {
@@ -361,17 +394,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int g = 0; g < kPanel / 16; ++g)
           if (g * 16 < ncols) tmem_ld16(taddr + c0 + g * 16, v + g * 16);
         tmem_ld_wait();
-        const float* bs = bias_s + as * 256 + c0;
+        const float* bs = bias_s + tab * 256 + c0;
+        const float* ss = scale_s + c0;
 #pragma unroll
         for (int j = 0; j < kPanel / 8; ++j) {
           if (j * 8 < ncols) {
             const float4 b0 = *reinterpret_cast<const float4*>(bs + j * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(bs + j * 8 + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(v[j * 8 + e]);
+            if constexpr (Epi::kScaled) {  // dequantise: acc * (activation row scale * weight column scale)
+              const float4 s0 = *reinterpret_cast<const float4*>(ss + j * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(ss + j * 8 + 4);
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[e] *= row_scale * sc[e];
+            }
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
-              const float2 r = bf16_round2(__uint_as_float(v[j * 8 + e]) + bb[e], __uint_as_float(v[j * 8 + e + 1]) + bb[e + 1]);
+              const float2 r = bf16_round2(acc[e] + bb[e], acc[e + 1] + bb[e + 1]);
               o[e] = live ? epi.act(r.x) : 0.f;
               o[e + 1] = live ? epi.act(r.y) : 0.f;
             }
@@ -398,6 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if constexpr (L::TAB_BUFS == 1) named_bar_sync(2, kEpiThreads);  // everyone is done with the single-buffered tables
     }
   }
 

@@ -51,14 +51,22 @@ def _cfg_value(cfg, name: str, aliases: Sequence[str] = ()):
     raise KeyError(f"audio config has no field {name!r}")
 
 
-def make_config(cfg, max_chunks: int = 0, max_tokens: int = 0) -> QasrConfig:
-    """From a HF ``audio_config`` (or a dict / the oracle's EncoderConfig) to the C struct."""
+QASR_FLAG_FP8, QASR_FLAG_FP8_PER_ROW = 1, 2
+_QUANT_FLAGS = {None: 0, "": 0, "bf16": 0, "fp8": QASR_FLAG_FP8, "fp8_per_tensor": QASR_FLAG_FP8,
+                "fp8_per_row": QASR_FLAG_FP8 | QASR_FLAG_FP8_PER_ROW}
+
+
+def make_config(cfg, max_chunks: int = 0, max_tokens: int = 0, quantize: str | None = None) -> QasrConfig:
+    """From a HF ``audio_config`` (or a dict / the oracle's EncoderConfig) to the C struct.
+    ``quantize``: None / "fp8" (per-tensor scales, the reference's QUANTIZE=fp8, src/server.py:362-371) / "fp8_per_row"."""
     alias = {
         "encoder_layers": ("layers",), "encoder_attention_heads": ("heads",), "encoder_ffn_dim": ("ffn",),
         "downsample_hidden_size": ("downsample_hidden",),
     }
     vals = {n: _cfg_value(cfg, n, alias.get(n, ())) for n in _CFG_FIELDS}
-    return QasrConfig(**vals, max_chunks=max_chunks, max_tokens=max_tokens, flags=0)
+    if quantize not in _QUANT_FLAGS:
+        raise QasrError(f"unknown quantize mode {quantize!r}; expected one of {sorted(k for k in _QUANT_FLAGS if k)}")
+    return QasrConfig(**vals, max_chunks=max_chunks, max_tokens=max_tokens, flags=_QUANT_FLAGS[quantize])
 
 
 def sinusoid_table(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
@@ -74,13 +82,14 @@ _DTYPES = {torch.float32: QASR_F32, torch.bfloat16: QASR_BF16, torch.float16: QA
 
 class B200AudioEncoder:
     def __init__(self, cfg, weights: Mapping[str, "torch.Tensor | np.ndarray"], device: int = 0,
-                 max_chunks: int = 0, max_tokens: int = 0):
+                 max_chunks: int = 0, max_tokens: int = 0, quantize: str | None = None):
         if not torch.cuda.is_available():
             raise QasrError("B200AudioEncoder needs a CUDA device; this backend has no CPU path")
         self.lib = load_library()
         self.device = int(device)
         self.tdev = torch.device("cuda", self.device)
-        self.cfg = make_config(cfg, max_chunks, max_tokens)
+        self.cfg = make_config(cfg, max_chunks, max_tokens, quantize)
+        self.quantize = quantize
         self.output_dim = int(self.cfg.output_dim)
         self.d_model = int(self.cfg.d_model)
         h = C.c_void_p()

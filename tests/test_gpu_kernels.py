@@ -147,3 +147,76 @@ def test_window_attention(lib, heads, lens):
     err = (out.float() - ref).abs().max().item()
     # P is rounded to bf16 before PV (as flash-attn does): ~2^-8 relative on a convex combination of |v| <~ 4
     assert err <= 0.03, err
+
+
+# ---------------------------------------------------------------------------------------------- fp8 (QUANTIZE=fp8 variant)
+def _quant_ref(x, per_row):
+    """torchao's dynamic e4m3 recipe on the CPU: scale = max(amax, 1e-12) / 448, q = e4m3_rn_sat(x / scale)."""
+    xf = x.float().cpu()
+    amax = xf.abs().amax(dim=1, keepdim=True) if per_row else xf.abs().amax().reshape(1, 1).expand(xf.shape[0], 1)
+    scale = amax.clamp(min=1e-12) / 448.0
+    q = (xf / scale).clamp(-448, 448).to(torch.float8_e4m3fn)
+    return q, scale.reshape(-1).contiguous()
+
+
+@pytest.mark.parametrize("per_row", [0, 1])
+@pytest.mark.parametrize("rows,k", [(5, 128), (300, 1024), (1000, 4096), (39, 7680)])
+def test_quant_fp8_kernel_bit_exact(lib, rows, k, per_row):
+    from qwen3_asr_b200._lib import check
+
+    g = torch.Generator().manual_seed(rows * 7 + k + per_row)
+    x = (torch.randn(rows, k, generator=g) * torch.logspace(-2, 1, rows)[:, None]).to(torch.bfloat16)
+    x[0, :8] = 0
+    if rows > 4:
+        x[3] = 0  # an all-zero row: scale clamps to 1e-12 / 448, q = 0
+    xd = x.cuda()
+    q = torch.zeros((rows, k), dtype=torch.uint8, device="cuda")
+    sc = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    check(lib, lib.qasr_debug_quant_fp8(_ptr(xd), rows, k, _ptr(q), _ptr(sc), per_row, _stream()), "qasr_debug_quant_fp8")
+    q_ref, sc_ref = _quant_ref(x, bool(per_row))
+    assert torch.equal(sc.cpu(), sc_ref)
+    assert torch.equal(q.cpu(), q_ref.view(torch.uint8))
+
+
+FP8_GEMM_SHAPES = [
+    # m, n, k, act, residual
+    (128, 128, 128, 0, False),
+    (300, 256, 1024, 1, False),
+    (77, 192, 256, 0, True),
+    (1000, 1024, 1024, 0, True),
+    (513, 3072, 1024, 0, False),
+    (390, 1024, 4096, 0, True),
+    (200, 896, 3584, 1, False),
+    (260, 1024, 7680, 0, False),
+]
+
+
+@pytest.mark.parametrize("m,n,k,act,res", FP8_GEMM_SHAPES)
+def test_gemm_fp8_tcgen05_vs_torch(lib, m, n, k, act, res):
+    """e4m3 x e4m3 tcgen05 GEMM (kind::f8f6f4) with row / column scales against the dequantised fp32 product."""
+    from qwen3_asr_b200._lib import check
+
+    g = torch.Generator().manual_seed(m + n + k)
+    a = (torch.randn(m, k, generator=g) * 3).clamp(-448, 448).to(torch.float8_e4m3fn)
+    b = (torch.randn(n, k, generator=g) * 3).clamp(-448, 448).to(torch.float8_e4m3fn)
+    rs = torch.rand(m, generator=g) * 0.02 + 0.001
+    cs = torch.rand(n, generator=g) * 0.02 + 0.001
+    bias = torch.randn(n, generator=g)
+    resid = torch.randn(m, n, generator=g).to(torch.bfloat16) if res else None
+    y = (a.float() @ b.float().t()) * rs[:, None] * cs[None, :] + bias
+    y = y.to(torch.bfloat16).float()
+    if act == 1:
+        y = torch.nn.functional.gelu(y).to(torch.bfloat16).float()
+    if res:
+        y = (y + resid.float()).to(torch.bfloat16).float()
+    d = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    rd = resid.cuda() if res else None
+    ad, bd, rsd, csd, biasd = a.view(torch.uint8).cuda(), b.view(torch.uint8).cuda(), rs.cuda(), cs.cuda(), bias.cuda()  # keep alive
+    check(lib, lib.qasr_debug_gemm_fp8(_ptr(ad), _ptr(bd), _ptr(rsd), _ptr(csd), _ptr(biasd), _ptr(rd), _ptr(d), m, n, k, act, _stream()),
+          "qasr_debug_gemm_fp8")
+    torch.cuda.synchronize()
+    got = d.float().cpu()
+    assert torch.isfinite(got).all()
+    # products of e4m3 values are exact in fp32; only the accumulation order differs -> at most a bf16 ulp after rounding
+    err = ((got - y).abs() / (y.abs() + 1e-2)).max().item()
+    assert err <= 2 ** -7, err
