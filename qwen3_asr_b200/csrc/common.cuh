@@ -78,6 +78,18 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
+// x / s for many x and one s: r = 1 / s once, then two FMAs give the correctly rounded quotient (q0 = x r; q = q0 + (x - q0 s) r),
+// i.e. what IEEE division returns, without the slow path of the generic division sequence (no denormals / overflow here:
+// s >= 1e-12 / 448 and |x / s| <= 448 by construction).
+struct FastDivisor {
+  float s, r;
+  __device__ __forceinline__ explicit FastDivisor(float scale) : s(scale), r(1.0f / scale) {}
+  __device__ __forceinline__ float div(float x) const {
+    const float q0 = x * r;
+    return fmaf(fmaf(-q0, s, x), r, q0);
+  }
+};
+
 // order-preserving float <-> uint32 map for atomicMax on floats of either sign
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   uint32_t b = __float_as_uint(f);

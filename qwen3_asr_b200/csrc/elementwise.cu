@@ -2,6 +2,8 @@
 // non-causal multi-head attention of the audio encoder.  Restates
 // transformers/models/qwen3_omni_moe/modeling_qwen3_omni_moe.py: conv2d1 :649,730; LayerNorm :576,580,647;
 // attention :496-565 / eager definition :471-493 with the per-window block-diagonal structure of :676-693.
+#include <cuda_fp8.h>
+
 #include <algorithm>
 
 #include "kernels.h"
@@ -89,9 +91,12 @@ __global__ void __launch_bounds__(256) conv1_kernel(const MelT* __restrict__ mel
 // ---------------------------------------------------------------------------------------------
 constexpr int LN_WARPS = 8;
 
-template <int NV>  // NV = ceil(d / 256): 8-element vectors per lane
+// FP8_OUT (QUANTIZE=fp8 variant, per-row scales): the bf16-rounded output row is quantised in the same pass -- row amax by
+// warp shuffle, scale = max(amax, 1e-12) / 448, e4m3 to q_out, scale to row_scale -- instead of being written as bf16.
+template <int NV, bool FP8_OUT>  // NV = ceil(d / 256): 8-element vectors per lane
 __global__ void __launch_bounds__(LN_WARPS * 32, 2) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                                  uint8_t* __restrict__ q_out, float* __restrict__ row_scale,
                                                                   int rows, int d, float eps) {
   const int lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * LN_WARPS;
@@ -147,19 +152,54 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2) layernorm_kernel(const __nv_
       }
     }
     const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
-    __nv_bfloat16* orow = out + static_cast<long long>(row) * d;
+    if constexpr (!FP8_OUT) {
+      __nv_bfloat16* orow = out + static_cast<long long>(row) * d;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int col = (i * 32 + lane) * 8;
-      if (col < d) {
-        float y[8];
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 8;
+        if (col < d) {
+          float y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * g[i][j] + b[i][j];
-        uint4 u;
-        u.x = pack_bf16x2(y[0], y[1]); u.y = pack_bf16x2(y[2], y[3]);
-        u.z = pack_bf16x2(y[4], y[5]); u.w = pack_bf16x2(y[6], y[7]);
-        *reinterpret_cast<uint4*>(orow + col) = u;
+          for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * g[i][j] + b[i][j];
+          uint4 u;
+          u.x = pack_bf16x2(y[0], y[1]); u.y = pack_bf16x2(y[2], y[3]);
+          u.z = pack_bf16x2(y[4], y[5]); u.w = pack_bf16x2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(orow + col) = u;
+        }
       }
+    } else {
+      float amax = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 8;
+        if (col < d) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 r = bf16_round2((v[i][j] - mean) * rstd * g[i][j] + b[i][j], (v[i][j + 1] - mean) * rstd * g[i][j + 1] + b[i][j + 1]);
+            v[i][j] = r.x;  // the module output as the next op sees it: bf16
+            v[i][j + 1] = r.y;
+            amax = fmaxf(amax, fmaxf(fabsf(r.x), fabsf(r.y)));
+          }
+        }
+      }
+      const float scale = fmaxf(warp_max(amax), 1e-12f) / 448.0f;
+      const FastDivisor sc(scale);
+      uint8_t* qrow = q_out + static_cast<long long>(row) * d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 8;
+        if (col < d) {
+          uint32_t w[2];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const unsigned short p0 = __nv_cvt_float2_to_fp8x2(make_float2(sc.div(v[i][4 * hh]), sc.div(v[i][4 * hh + 1])), __NV_SATFINITE, __NV_E4M3);
+            const unsigned short p1 = __nv_cvt_float2_to_fp8x2(make_float2(sc.div(v[i][4 * hh + 2]), sc.div(v[i][4 * hh + 3])), __NV_SATFINITE, __NV_E4M3);
+            w[hh] = static_cast<uint32_t>(p0) | (static_cast<uint32_t>(p1) << 16);
+          }
+          *reinterpret_cast<uint2*>(qrow + col) = make_uint2(w[0], w[1]);
+        }
+      }
+      if (lane == 0) row_scale[row] = scale;
     }
   }
 }
@@ -326,18 +366,33 @@ cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, con
   return cudaGetLastError();
 }
 
+namespace {
+template <bool FP8_OUT>
+cudaError_t launch_ln(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* out, uint8_t* q_out, float* row_scale,
+                      int rows, int d, float eps, cudaStream_t stream) {
+  // ~5 rows per warp at the C2 batch (12480 rows): enough rows to amortise the gamma/beta registers, enough warps to fill the chip
+  const int grid = std::max(1, std::min((rows + LN_WARPS - 1) / LN_WARPS, 2 * kNumSMs));
+  const int nv = (d + 255) / 256;
+  if (nv <= 1) layernorm_kernel<1, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
+  else if (nv <= 2) layernorm_kernel<2, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
+  else if (nv <= 4) layernorm_kernel<4, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
+  else layernorm_kernel<8, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
+  return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_layernorm(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int d,
                              float eps, cudaStream_t stream) {
   if (rows == 0) return cudaSuccess;
   if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;
-  // ~5 rows per warp at the C2 batch (12480 rows): enough rows to amortise the gamma/beta registers, enough warps to fill the chip
-  const int grid = std::max(1, std::min((rows + LN_WARPS - 1) / LN_WARPS, 2 * kNumSMs));
-  const int nv = (d + 255) / 256;
-  if (nv <= 1) layernorm_kernel<1><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
-  else if (nv <= 2) layernorm_kernel<2><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
-  else if (nv <= 4) layernorm_kernel<4><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
-  else layernorm_kernel<8><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, rows, d, eps);
-  return cudaGetLastError();
+  return launch_ln<false>(x, gamma, beta, out, nullptr, nullptr, rows, d, eps, stream);
+}
+
+cudaError_t launch_layernorm_fp8(const __nv_bfloat16* x, const float* gamma, const float* beta, uint8_t* q_out, float* row_scale, int rows,
+                                 int d, float eps, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;
+  return launch_ln<true>(x, gamma, beta, nullptr, q_out, row_scale, rows, d, eps, stream);
 }
 
 cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len, int d,

@@ -419,35 +419,46 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
 
   // ---- transformer layers
   // one nn.Linear: (fp8: quantise the bf16 input first) GEMM with fused bias / GELU / residual epilogue
+  // a_raw == nullptr: the producer (LayerNorm) has already left the quantised input and its row scales in h->a8 / h->a_scale
   auto linear = [&](const char* name, double flops, const CUtensorMap* tm_a, const bf16* a_raw, const LinearW& w, int epi, bf16* o,
                     long long ldo, const bf16* residual) -> int {
     LinearArgs la{};
     la.tm_a = tm_a; la.tm_b = &w.tm; la.bn = w.bn; la.a = a_raw; la.lda = w.k; la.b = w.w; la.ldb = w.k;
     la.m = ntok; la.n = w.n; la.k = w.k; la.epi = epi; la.out = o; la.ldo = ldo; la.bias = w.b; la.residual = residual;
     if (h->fp8) {
-      QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(a_raw, ntok, w.k));
+      if (a_raw != nullptr) QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(a_raw, ntok, w.k));
       la.tm_a = w.k == d ? &h->tm_a8_d : &h->tm_a8_ffn;
       la.fp8 = 1; la.row_scale = h->a_scale; la.col_scale = w.wscale;
     }
     QASR_LAUNCH(h, name, flops, stream, gemm_linear(la, h->simt, h->num_sms, stream));
     return 0;
   };
+  // LayerNorm feeding a Linear: bf16 row to hbuf, or (fp8 per-row) straight to e4m3 + row scale -> returns the Linear's input
+  const bool ln_fused_quant = h->fp8 && h->fp8_per_row;
+  auto layernorm = [&](const float* g, const float* b) -> int {
+    if (ln_fused_quant)
+      QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm_fp8(h->x, g, b, h->a8, h->a_scale, ntok, d, 1e-5f, stream));
+    else
+      QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, g, b, h->hbuf, ntok, d, 1e-5f, stream));
+    return 0;
+  };
+  const bf16* ln_out = ln_fused_quant ? nullptr : h->hbuf;
   const int n_win = static_cast<int>(mb.win.size());
   int rc;
   for (const LayerW& L : h->layers) {
     const double tk = 2.0 * ntok;
-    QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, L.ln1_g, L.ln1_b, h->hbuf, ntok, d, 1e-5f, stream));
-    if ((rc = linear("qkv_gemm", tk * 3 * d * d, &h->tm_h, h->hbuf, L.qkv, LIN_PLAIN, h->qkv, 3LL * d, nullptr)) != 0) return rc;
+    if ((rc = layernorm(L.ln1_g, L.ln1_b)) != 0) return rc;
+    if ((rc = linear("qkv_gemm", tk * 3 * d * d, &h->tm_h, ln_out, L.qkv, LIN_PLAIN, h->qkv, 3LL * d, nullptr)) != 0) return rc;
     QASR_LAUNCH(h, "window_attention", att_flops, stream,
                 launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, stream));
     if ((rc = linear("out_proj_gemm", tk * d * d, &h->tm_att, h->att, L.out, LIN_RESIDUAL, h->x, d, h->x)) != 0) return rc;
-    QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, L.ln2_g, L.ln2_b, h->hbuf, ntok, d, 1e-5f, stream));
-    if ((rc = linear("fc1_gemm", tk * d * c.encoder_ffn_dim, &h->tm_h, h->hbuf, L.fc1, LIN_GELU, h->ffn, c.encoder_ffn_dim, nullptr)) != 0) return rc;
+    if ((rc = layernorm(L.ln2_g, L.ln2_b)) != 0) return rc;
+    if ((rc = linear("fc1_gemm", tk * d * c.encoder_ffn_dim, &h->tm_h, ln_out, L.fc1, LIN_GELU, h->ffn, c.encoder_ffn_dim, nullptr)) != 0) return rc;
     if ((rc = linear("fc2_gemm", tk * d * c.encoder_ffn_dim, &h->tm_ffn, h->ffn, L.fc2, LIN_RESIDUAL, h->x, d, h->x)) != 0) return rc;
   }
   // ---- output head
-  QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, h->lnp_g, h->lnp_b, h->hbuf, ntok, d, 1e-5f, stream));
-  if ((rc = linear("proj1_gemm", 2.0 * ntok * d * d, &h->tm_h, h->hbuf, h->proj1, LIN_GELU, h->att, d, nullptr)) != 0) return rc;
+  if ((rc = layernorm(h->lnp_g, h->lnp_b)) != 0) return rc;
+  if ((rc = linear("proj1_gemm", 2.0 * ntok * d * d, &h->tm_h, ln_out, h->proj1, LIN_GELU, h->att, d, nullptr)) != 0) return rc;
   if ((rc = linear("proj2_gemm", 2.0 * ntok * d * c.output_dim, &h->tm_att, h->att, h->proj2, LIN_PLAIN, out, c.output_dim, nullptr)) != 0) return rc;
 
   QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));

@@ -26,9 +26,9 @@ __device__ __forceinline__ float amax8(const uint4& u) {
   float2 c = unpack_bf16x2(u.z & 0x7fff7fffu), d = unpack_bf16x2(u.w & 0x7fff7fffu);
   return fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(fmaxf(c.x, c.y), fmaxf(d.x, d.y)));
 }
-__device__ __forceinline__ uint32_t quant4(float2 lo, float2 hi, float scale) {
-  const unsigned short p0 = __nv_cvt_float2_to_fp8x2(make_float2(lo.x / scale, lo.y / scale), __NV_SATFINITE, __NV_E4M3);
-  const unsigned short p1 = __nv_cvt_float2_to_fp8x2(make_float2(hi.x / scale, hi.y / scale), __NV_SATFINITE, __NV_E4M3);
+__device__ __forceinline__ uint32_t quant4(float2 lo, float2 hi, const FastDivisor& sc) {
+  const unsigned short p0 = __nv_cvt_float2_to_fp8x2(make_float2(sc.div(lo.x), sc.div(lo.y)), __NV_SATFINITE, __NV_E4M3);
+  const unsigned short p1 = __nv_cvt_float2_to_fp8x2(make_float2(sc.div(hi.x), sc.div(hi.y)), __NV_SATFINITE, __NV_E4M3);
   return static_cast<uint32_t>(p0) | (static_cast<uint32_t>(p1) << 16);
 }
 
@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(Q_WARPS * 32) quant_rows_kernel(const __nv_bfl
       scale = fmaxf(warp_max(m), kAmaxEps) / kE4M3Max;
     }
     uint2* dst = reinterpret_cast<uint2*>(q + static_cast<long long>(row) * ldq);
+    const FastDivisor sc(scale);
     for (int v = lane; v < vecs; v += 32) {
       const uint4 u = src[v];  // second touch of the row: L1 / L2 hit
       uint2 o;
-      o.x = quant4(unpack_bf16x2(u.x), unpack_bf16x2(u.y), scale);
-      o.y = quant4(unpack_bf16x2(u.z), unpack_bf16x2(u.w), scale);
+      o.x = quant4(unpack_bf16x2(u.x), unpack_bf16x2(u.y), sc);
+      o.y = quant4(unpack_bf16x2(u.z), unpack_bf16x2(u.w), sc);
       dst[v] = o;
     }
     if (lane == 0) row_scale[row] = scale;
