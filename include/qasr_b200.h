@@ -173,6 +173,10 @@ QASR_API int qasr_debug_gemm_fp8(const void* a8, const void* b8, const float* ro
 QASR_API int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int d, void* stream);
 QASR_API int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream);
 
+/* The tcgen05 attention kernel (windows <= 128 tokens); qkv has `tokens` rows. */
+QASR_API int qasr_debug_attention_tc(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int tokens, int d, int heads,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

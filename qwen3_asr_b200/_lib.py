@@ -60,6 +60,7 @@ SIGNATURES = {
     "qasr_debug_gemm_fp8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "qasr_debug_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "qasr_debug_attention": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, _P]),
+    "qasr_debug_attention_tc": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 
 _lib = None

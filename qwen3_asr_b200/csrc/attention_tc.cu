@@ -1,0 +1,271 @@
+// Windowed (block-diagonal, non-causal) multi-head attention on the tcgen05 tensor cores.
+//
+// Restates Qwen3OmniMoeAudioAttention (transformers modeling_qwen3_omni_moe.py:496-565, eager definition :471-493) under the
+// per-window cu_seqlens of :745-752 -- what the reference deployment gets from flash-attn varlen: for every window (<= 104
+// tokens with n_window_infer = 800; up to 128 supported here) and head, softmax(q k^T / sqrt(64)) v with fp32 softmax and the
+// un-normalised probabilities rounded to bf16 for the second product (flash-attn's rounding point).
+//
+// One persistent CTA per SM walks (window, head) items.  Per item everything stays on chip:
+//   warp 0        TMA: Q, K, V tiles [128 tokens x 64 dims] of the packed qkv activation -> 128B-swizzled smem (2 stages)
+//   warp 1        MMA issuer: S = Q K^T (kind::f16, M = 128, N = keys rounded to 16, K = 64) into TMEM;
+//                 O = P V with P read from TMEM (A operand) and V used as an MN-major B operand straight from its
+//                 row-major tile -- no transposes, no smem round trip for S or P
+//   warp 2        TMEM allocation (2 slots x (128 S/P columns + 64 O columns))
+//   warps 4-7 / 8-11   two softmax warpgroups (thread = query row) alternating over items: tcgen05.ld S -> mask -> max ->
+//                 exp2 -> row sum -> bf16 P back into the S columns (tcgen05.st) -> after the second MMA, O / sum -> bf16 -> HBM
+// so the tensor core runs item i+1's QK^T while warpgroup A is in item i's softmax and warpgroup B finishes item i-1.
+#include <algorithm>
+
+#include "kernels.h"
+#include "tc_gemm.cuh"
+
+namespace qasr {
+namespace {
+
+using namespace tc;
+
+constexpr int AT_THREADS = 12 * 32;
+constexpr int AT_HD = 64;
+constexpr int AT_ROWS = 128;                      // tokens per tile (window length <= 128)
+constexpr int AT_TILE_BYTES = AT_ROWS * AT_HD * 2;  // 16 KB
+constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;   // Q, K, V
+constexpr int AT_STAGES = 2;
+constexpr int AT_SLOT_COLS = 192;                 // TMEM: 128 columns S (P aliases the first 64) + 64 columns O
+constexpr int AT_SMEM = AT_STAGES * AT_STAGE_BYTES + 256;
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void at_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      printf("qasr attention: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// bf16 x bf16 -> fp32, A K-major (or TMEM), B K-major (b_mn = 0) or MN-major (b_mn = 1)
+__device__ __forceinline__ uint32_t at_idesc(int n, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(AT_ROWS >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __restrict__ win, int n_win, int heads, int d,
+                    __nv_bfloat16* __restrict__ out, float scale_log2e) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_STAGES * AT_STAGE_BYTES);
+  uint64_t* full_bar = bars;            // [2] TMA -> MMA: Q, K, V of the stage have landed
+  uint64_t* empty_bar = bars + 2;       // [2] MMA -> TMA: both products of the item have read the stage
+  uint64_t* s_full = bars + 4;          // [2] MMA -> softmax: S is in TMEM
+  uint64_t* p_full = bars + 6;          // [2] softmax -> MMA: P is in TMEM
+  uint64_t* o_full = bars + 8;          // [2] MMA -> softmax: O is in TMEM
+  uint64_t* slot_empty = bars + 10;     // [2] softmax -> MMA: the slot's S/P/O columns are drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = n_win * heads;
+
+  if (warp == 0 && lane == 0) prefetch_tmap(&tm_qkv);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);      // one elected lane per softmax warp
+      mbar_init(&o_full[i], 1);
+      mbar_init(&slot_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      at_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
+        const int w = item / heads, h = item - w * heads;
+        const int row0 = __ldg(&win[w]).x;
+        uint8_t* st = smem + s * AT_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], AT_STAGE_BYTES);
+        tma_load_2d(st, &tm_qkv, h * AT_HD, row0, &full_bar[s]);
+        tma_load_2d(st + AT_TILE_BYTES, &tm_qkv, d + h * AT_HD, row0, &full_bar[s]);
+        tma_load_2d(st + 2 * AT_TILE_BYTES, &tm_qkv, 2 * d + h * AT_HD, row0, &full_bar[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // software-pipelined: S(i+1) = Q K^T is issued before O(i) = P V, so the tensor core has work while item i is in softmax
+    const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem));
+    auto issue_qk = [&](int it, int item) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int wl = __ldg(&win[item / heads]).y;
+      const int n16 = (wl + 15) >> 4;
+      at_wait(&full_bar[s], ph);
+      at_wait(&slot_empty[s], ph ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dq = desc0 + static_cast<uint64_t>((s * AT_STAGE_BYTES) >> 4);
+        const uint64_t dk = dq + static_cast<uint64_t>(AT_TILE_BYTES >> 4);
+        const uint32_t idesc = at_idesc(n16 * 16, 0);
+        const uint32_t t_s = tmem_base + static_cast<uint32_t>(s * AT_SLOT_COLS);
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) umma<K_BF16>(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[s]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int it, int item) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int wl = __ldg(&win[item / heads]).y;
+      const int n16 = (wl + 15) >> 4;
+      at_wait(&p_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dv = desc0 + static_cast<uint64_t>((s * AT_STAGE_BYTES + 2 * AT_TILE_BYTES) >> 4);
+        const uint32_t idesc = at_idesc(AT_HD, 1);
+        const uint32_t t_p = tmem_base + static_cast<uint32_t>(s * AT_SLOT_COLS);
+        const uint32_t t_o = t_p + 128;
+        for (int k = 0; k < n16; ++k)  // 16 keys per step: 8 packed-bf16 columns of P, 16 rows (2048 bytes) of V
+          umma_bf16_ts(t_o, t_p + static_cast<uint32_t>(8 * k), dv + static_cast<uint64_t>(128 * k), idesc, k != 0 ? 1u : 0u);
+        umma_commit(&o_full[s]);
+        umma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    };
+    int it = 0, prev_item = -1;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      issue_qk(it, item);
+      if (prev_item >= 0) issue_pv(it - 1, prev_item);
+      prev_item = item;
+    }
+    if (prev_item >= 0) issue_pv(it - 1, prev_item);
+  } else if (warp >= 4) {
+    // ===================== softmax + output warpgroups =====================
+    const int wg = (warp - 4) >> 2;            // 0 / 1: this warpgroup serves items whose slot == wg
+    const int q = warp & 3;                    // TMEM lane quarter of this warp
+    const int row = q * 32 + lane;             // query row == TMEM lane
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      if ((it & 1) != wg) continue;
+      const uint32_t ph = (it >> 1) & 1;
+      const int w = item / heads, h = item - w * heads;
+      const int2 wd = __ldg(&win[w]);
+      const int wl = wd.y;
+      const int n16 = (wl + 15) >> 4;
+      const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(wg * AT_SLOT_COLS);
+
+      at_wait(&s_full[wg], ph);
+      tc_fence_after();
+      // pass 1: row max over the live keys
+      float mx = -INFINITY;
+      for (int g = 0; g < n16; ++g) {
+        uint32_t v[16];
+        tmem_ld16(t_s + g * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, g * 16 + j < wl ? __uint_as_float(v[j]) : -INFINITY);
+      }
+      // pass 2: p = exp2((s - max) * scale), row sum in fp32, bf16 pairs back into the slot's first columns
+      const float mscaled = mx * scale_log2e;
+      float sum = 0.f;
+      for (int g = 0; g < n16; ++g) {
+        uint32_t v[16], pk[8];
+        tmem_ld16(t_s + g * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float p0 = g * 16 + j < wl ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mscaled)) : 0.f;
+          const float p1 = g * 16 + j + 1 < wl ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mscaled)) : 0.f;
+          sum += p0 + p1;
+          pk[j >> 1] = pack_bf16x2(p0, p1);
+        }
+        // P columns [8g, 8g+8) overwrite S columns that this thread has already consumed (8g + 8 <= 16 (g + 1))
+        tmem_st8(t_s + g * 8, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[wg]);
+
+      // O = P V is ready: normalise, round, store this row's 64 dims (128 contiguous bytes)
+      at_wait(&o_full[wg], ph);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* orow = out + (static_cast<long long>(wd.x) + row) * d + h * AT_HD;
+#pragma unroll
+      for (int g = 0; g < AT_HD / 16; ++g) {
+        uint32_t v[16];
+        tmem_ld16(t_s + 128 + g * 16, v);
+        tmem_ld_wait();
+        if (row < wl) {
+          uint4 a, b;
+          a.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+          a.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+          a.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+          a.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+          b.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+          b.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+          b.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+          b.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+          reinterpret_cast<uint4*>(orow + g * 16)[0] = a;
+          reinterpret_cast<uint4*>(orow + g * 16)[1] = b;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_empty[wg]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// tm_qkv: make_tmap_rowmajor over the packed qkv activation [tokens, 3 d] with box rows = 128
+cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len, int d,
+                                       int heads, int num_sms, cudaStream_t stream) {
+  if (n_win == 0) return cudaSuccess;
+  if (d != heads * AT_HD || max_win_len > AT_ROWS) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  if (e != cudaSuccess) return e;
+  const float scale_log2e = 0.125f * 1.44269504088896340736f;  // head_dim^-0.5 * log2(e)
+  const int grid = std::min(n_win * heads, num_sms);
+  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, out, scale_log2e);
+  return cudaGetLastError();
+}
+
+}  // namespace qasr

@@ -6,6 +6,8 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 
+#include <cuda.h>
+
 #include "mel.cuh"
 
 namespace qasr {
@@ -51,5 +53,9 @@ cudaError_t launch_layernorm_fp8(const __nv_bfloat16* x, const float* gamma, con
 // qkv: [tokens, 3d] (q | k | v, head h at columns h*64); out: [tokens, d]; win: [n_win] (start, len)
 cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* win, int n_win,
                                     int max_win_len, int d, int heads, cudaStream_t stream);
+
+// tcgen05 version (attention_tc.cu): windows up to 128 tokens; tm_qkv = 128B-swizzled map over qkv [tokens, 3d], box 64 x 128
+cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len,
+                                       int d, int heads, int num_sms, cudaStream_t stream);
 
 }  // namespace qasr

@@ -123,7 +123,8 @@ struct qasr_handle_s {
   // workspace
   bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr;
   bf16 *x = nullptr, *hbuf = nullptr, *qkv = nullptr, *att = nullptr, *ffn = nullptr, *embed_dbg = nullptr;
-  CUtensorMap tm_act1, tm_act2, tm_act3, tm_h, tm_att, tm_ffn;
+  CUtensorMap tm_act1, tm_act2, tm_act3, tm_h, tm_att, tm_ffn, tm_qkv;
+  bool attn_simt = false;   // QASR_ATTENTION=mma_sync: the mma.sync attention kernel instead of the tcgen05 one
   // fp8 mode: the quantised copy of whichever activation feeds the next Linear, its row scales, per-call amax slots
   uint8_t* a8 = nullptr;
   float* a_scale = nullptr;
@@ -449,8 +450,12 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     const double tk = 2.0 * ntok;
     if ((rc = layernorm(L.ln1_g, L.ln1_b)) != 0) return rc;
     if ((rc = linear("qkv_gemm", tk * 3 * d * d, &h->tm_h, ln_out, L.qkv, LIN_PLAIN, h->qkv, 3LL * d, nullptr)) != 0) return rc;
-    QASR_LAUNCH(h, "window_attention", att_flops, stream,
-                launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, stream));
+    if (mb.max_win <= 128 && !h->attn_simt)
+      QASR_LAUNCH(h, "window_attention", att_flops, stream,
+                  launch_window_attention_tc(&h->tm_qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, h->num_sms, stream));
+    else
+      QASR_LAUNCH(h, "window_attention", att_flops, stream,
+                  launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, stream));
     if ((rc = linear("out_proj_gemm", tk * d * d, &h->tm_att, h->att, L.out, LIN_RESIDUAL, h->x, d, h->x)) != 0) return rc;
     if ((rc = layernorm(L.ln2_g, L.ln2_b)) != 0) return rc;
     if ((rc = linear("fc1_gemm", tk * d * c.encoder_ffn_dim, &h->tm_h, ln_out, L.fc1, LIN_GELU, h->ffn, c.encoder_ffn_dim, nullptr)) != 0) return rc;
@@ -522,6 +527,8 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
     delete h;
     return 1;
   }
+  e = std::getenv("QASR_ATTENTION");
+  h->attn_simt = e != nullptr && std::string(e) == "mma_sync";
   e = std::getenv("QASR_DEBUG_KEEP");
   h->keep_debug = e != nullptr && e[0] == '1';
 
@@ -691,6 +698,9 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = make_tmap_rowmajor(&h->tm_h, h->hbuf, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_att, h->att, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_ffn, h->ffn, mt, ffn, ffn, 128)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor(&h->tm_qkv, h->qkv, mt, 3LL * d, 3LL * d, 128)) != 0) return rc;
+  // the tcgen05 attention multiplies V rows past a window's end by exact zeros: they must never hold NaN / Inf bit patterns
+  QASR_CUDA_CHECK(cudaMemset(h->qkv, 0, mt * 3 * d * sizeof(bf16)));
   if (h->fp8) {
     QASR_REQUIRE(d % 128 == 0 && ffn % 128 == 0, "fp8 mode needs d_model and encoder_ffn_dim to be multiples of 128");
     const size_t rows_conv = align_up(mc * kTokPerChunk, 128);
@@ -1156,6 +1166,31 @@ int qasr_debug_gemm_fp8(const void* a8, const void* b8, const float* row_scale, 
 int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int d, void* stream) {
   QASR_CUDA_CHECK(launch_layernorm(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(out), rows, d, 1e-5f,
                                    static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int qasr_debug_attention_tc(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int tokens, int d, int heads,
+                            void* stream_v) {
+  QASR_REQUIRE(qkv != nullptr && out != nullptr && win_start_len_host != nullptr && n_win > 0 && tokens > 0, "qasr_debug_attention_tc: bad argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  CUtensorMap tm;
+  int rc;
+  if ((rc = make_tmap_rowmajor(&tm, qkv, tokens, 3LL * d, 3LL * d, 128)) != 0) return rc;
+  int dev = 0, sms = kNumSMs;
+  QASR_CUDA_CHECK(cudaGetDevice(&dev));
+  QASR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int2* dwin = nullptr;
+  QASR_CUDA_CHECK(cudaMalloc(&dwin, n_win * sizeof(int2)));
+  int max_win = 0;
+  for (int i = 0; i < n_win; ++i) max_win = std::max(max_win, win_start_len_host[2 * i + 1]);
+  cudaError_t e = cudaMemcpyAsync(dwin, win_start_len_host, n_win * sizeof(int2), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = launch_window_attention_tc(&tm, static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, sms, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(dwin);
+  if (e != cudaSuccess) {
+    set_last_error(std::string("qasr_debug_attention_tc: ") + cudaGetErrorString(e));
+    return 2;
+  }
   return 0;
 }
 

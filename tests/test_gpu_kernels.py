@@ -124,8 +124,10 @@ def _attention_ref(qkv, wins, d, heads):
     return out
 
 
-@pytest.mark.parametrize("heads,lens", [(2, [6]), (2, [104, 33]), (16, [104, 104, 104, 78, 1, 13, 17]), (14, [104, 65, 104])])
-def test_window_attention(lib, heads, lens):
+@pytest.mark.parametrize("impl", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("heads,lens", [(2, [6]), (2, [104, 33]), (16, [104, 104, 104, 78, 1, 13, 17]), (14, [104, 65, 104]), (2, [128, 127, 16, 15]),
+                                        (16, [104] * 40 + [78] * 10)])
+def test_window_attention(lib, heads, lens, impl):
     from qwen3_asr_b200._lib import check
 
     d = heads * 64
@@ -140,7 +142,10 @@ def test_window_attention(lib, heads, lens):
         s += wl
     win_host = (C.c_int32 * (2 * len(wins)))(*[v for w in wins for v in w])
     out = torch.full((n, d), float("nan"), dtype=torch.bfloat16, device="cuda")
-    check(lib, lib.qasr_debug_attention(_ptr(qkv), _ptr(out), win_host, len(wins), d, heads, _stream()), "attention")
+    if impl == "tcgen05":
+        check(lib, lib.qasr_debug_attention_tc(_ptr(qkv), _ptr(out), win_host, len(wins), n, d, heads, _stream()), "attention_tc")
+    else:
+        check(lib, lib.qasr_debug_attention(_ptr(qkv), _ptr(out), win_host, len(wins), d, heads, _stream()), "attention")
     torch.cuda.synchronize()
     ref = _attention_ref(qkv, wins, d, heads)
     assert torch.isfinite(out.float()).all()
