@@ -6,7 +6,8 @@
 // un-normalised probabilities rounded to bf16 for the second product (flash-attn's rounding point).
 //
 // One persistent CTA per SM walks (window, head) items.  Per item everything stays on chip:
-//   warp 0        TMA: Q, K, V tiles [128 tokens x 64 dims] of the packed qkv activation -> 128B-swizzled smem (2 stages)
+//   warp 0        TMA: Q, K, V tiles [128 tokens x 64 dims] of the head-major qkv activation (one contiguous 16 KB block each)
+//                 -> 128B-swizzled smem (4-stage ring)
 //   warp 1        MMA issuer: S = Q K^T (kind::f16, M = 128, N = keys rounded to 16, K = 64) into TMEM;
 //                 O = P V with P read from TMEM (A operand) and V used as an MN-major B operand straight from its
 //                 row-major tile -- no transposes, no smem round trip for S or P
@@ -29,9 +30,10 @@ constexpr int AT_HD = 64;
 constexpr int AT_ROWS = 128;                      // tokens per tile (window length <= 128)
 constexpr int AT_TILE_BYTES = AT_ROWS * AT_HD * 2;  // 16 KB
 constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;   // Q, K, V
-constexpr int AT_STAGES = 2;
+constexpr int AT_STAGES = 4;                      // smem ring (TMA runs up to 4 items ahead); TMEM slots alternate per item
 constexpr int AT_SLOT_COLS = 192;                 // TMEM: 128 columns S (P aliases the first 64) + 64 columns O
 constexpr int AT_SMEM = AT_STAGES * AT_STAGE_BYTES + 256;
+static_assert(AT_SMEM <= 232448, "exceeds the shared memory a CTA can opt in to");
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -67,30 +69,32 @@ __device__ __forceinline__ uint32_t at_idesc(int n, int b_mn) {
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __restrict__ win, int n_win, int heads, int d,
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __restrict__ win, int n_win, int heads, int d, int head_rows,
                     __nv_bfloat16* __restrict__ out, float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_STAGES * AT_STAGE_BYTES);
-  uint64_t* full_bar = bars;            // [2] TMA -> MMA: Q, K, V of the stage have landed
-  uint64_t* empty_bar = bars + 2;       // [2] MMA -> TMA: both products of the item have read the stage
-  uint64_t* s_full = bars + 4;          // [2] MMA -> softmax: S is in TMEM
-  uint64_t* p_full = bars + 6;          // [2] softmax -> MMA: P is in TMEM
-  uint64_t* o_full = bars + 8;          // [2] MMA -> softmax: O is in TMEM
-  uint64_t* slot_empty = bars + 10;     // [2] softmax -> MMA: the slot's S/P/O columns are drained
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* full_bar = bars;                    // [STAGES] TMA -> MMA: Q, K, V of the stage have landed
+  uint64_t* empty_bar = bars + AT_STAGES;       // [STAGES] MMA -> TMA: both products of the item have read the stage
+  uint64_t* s_full = bars + 2 * AT_STAGES;      // [2] MMA -> softmax: S is in TMEM
+  uint64_t* p_full = s_full + 2;                // [2] softmax -> MMA: P is in TMEM
+  uint64_t* o_full = s_full + 4;                // [2] MMA -> softmax: O is in TMEM
+  uint64_t* o_empty = s_full + 6;               // [2] softmax -> MMA: the slot's O columns are drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_win * heads;
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tm_qkv);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < AT_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);      // one elected lane per softmax warp
       mbar_init(&o_full[i], 1);
-      mbar_init(&slot_empty[i], 4);
+      mbar_init(&o_empty[i], 4);
     }
     fence_barrier_init();
   }
@@ -104,58 +108,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
     // ===================== TMA producer =====================
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+      const int s = it % AT_STAGES;
+      const uint32_t ph = (it / AT_STAGES) & 1;
       at_wait(&empty_bar[s], ph ^ 1);
       if (elect_one()) {
         const int w = item / heads, h = item - w * heads;
         const int row0 = __ldg(&win[w]).x;
         uint8_t* st = smem + s * AT_STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], AT_STAGE_BYTES);
-        tma_load_2d(st, &tm_qkv, h * AT_HD, row0, &full_bar[s]);
-        tma_load_2d(st + AT_TILE_BYTES, &tm_qkv, d + h * AT_HD, row0, &full_bar[s]);
-        tma_load_2d(st + 2 * AT_TILE_BYTES, &tm_qkv, 2 * d + h * AT_HD, row0, &full_bar[s]);
+        // head-major qkv: plane (section, head) holds that head's [tokens, 64] rows back to back -> one contiguous 16 KB block
+        tma_load_2d(st, &tm_qkv, 0, h * head_rows + row0, &full_bar[s]);
+        tma_load_2d(st + AT_TILE_BYTES, &tm_qkv, 0, (heads + h) * head_rows + row0, &full_bar[s]);
+        tma_load_2d(st + 2 * AT_TILE_BYTES, &tm_qkv, 0, (2 * heads + h) * head_rows + row0, &full_bar[s]);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // software-pipelined: S(i+1) = Q K^T is issued before O(i) = P V, so the tensor core has work while item i is in softmax
+    // software-pipelined: S(i+1) = Q K^T is issued before O(i) = P V, so the tensor core has work while item i is in softmax.
+    // tcgen05 operations execute in issue order: S(i+2) may overwrite the slot's S/P columns as soon as P V(i) has been
+    // issued -- only the O columns have to wait for the softmax warpgroup (o_empty).
     const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem));
     auto issue_qk = [&](int it, int item) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+      const int s = it % AT_STAGES, t = it & 1;
+      const uint32_t ph = (it / AT_STAGES) & 1;
       const int wl = __ldg(&win[item / heads]).y;
       const int n16 = (wl + 15) >> 4;
       at_wait(&full_bar[s], ph);
-      at_wait(&slot_empty[s], ph ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dq = desc0 + static_cast<uint64_t>((s * AT_STAGE_BYTES) >> 4);
         const uint64_t dk = dq + static_cast<uint64_t>(AT_TILE_BYTES >> 4);
         const uint32_t idesc = at_idesc(n16 * 16, 0);
-        const uint32_t t_s = tmem_base + static_cast<uint32_t>(s * AT_SLOT_COLS);
+        const uint32_t t_s = tmem_base + static_cast<uint32_t>(t * AT_SLOT_COLS);
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k) umma<K_BF16>(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[s]);
+        umma_commit(&s_full[t]);
       }
       __syncwarp();
     };
     auto issue_pv = [&](int it, int item) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+      const int s = it % AT_STAGES, t = it & 1;
+      const uint32_t pht = (it >> 1) & 1;
       const int wl = __ldg(&win[item / heads]).y;
       const int n16 = (wl + 15) >> 4;
-      at_wait(&p_full[s], ph);
+      at_wait(&p_full[t], pht);
+      at_wait(&o_empty[t], pht ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dv = desc0 + static_cast<uint64_t>((s * AT_STAGE_BYTES + 2 * AT_TILE_BYTES) >> 4);
         const uint32_t idesc = at_idesc(AT_HD, 1);
-        const uint32_t t_p = tmem_base + static_cast<uint32_t>(s * AT_SLOT_COLS);
+        const uint32_t t_p = tmem_base + static_cast<uint32_t>(t * AT_SLOT_COLS);
         const uint32_t t_o = t_p + 128;
         for (int k = 0; k < n16; ++k)  // 16 keys per step: 8 packed-bf16 columns of P, 16 rows (2048 bytes) of V
           umma_bf16_ts(t_o, t_p + static_cast<uint32_t>(8 * k), dv + static_cast<uint64_t>(128 * k), idesc, k != 0 ? 1u : 0u);
-        umma_commit(&o_full[s]);
+        umma_commit(&o_full[t]);
         umma_commit(&empty_bar[s]);
       }
       __syncwarp();
@@ -184,32 +191,81 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
 
       at_wait(&s_full[wg], ph);
       tc_fence_after();
-      // pass 1: row max over the live keys
-      float mx = -INFINITY;
-      for (int g = 0; g < n16; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_s + g * 16, v);
-        tmem_ld_wait();
+      // Two passes over the S row (max, then exp), each walking 32-column batches with the NEXT batch's tcgen05.ld already in
+      // flight while the current one is processed, so TMEM latency is exposed once per pass rather than once per 16 columns.
+      // Only the last 16-key granule can hold keys past the window's end.
+      const int tail = wl - (n16 - 1) * 16;  // live keys in the last granule, 1..16
+      uint32_t buf[2][32];
+      auto load_batch = [&](int b) {  // granules 2b and 2b+1
+        tmem_ld16(t_s + b * 32, buf[b & 1]);
+        if (2 * b + 1 < n16) tmem_ld16(t_s + b * 32 + 16, buf[b & 1] + 16);
+      };
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      load_batch(0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, g * 16 + j < wl ? __uint_as_float(v[j]) : -INFINITY);
-      }
-      // pass 2: p = exp2((s - max) * scale), row sum in fp32, bf16 pairs back into the slot's first columns
-      const float mscaled = mx * scale_log2e;
-      float sum = 0.f;
-      for (int g = 0; g < n16; ++g) {
-        uint32_t v[16], pk[8];
-        tmem_ld16(t_s + g * 16, v);
-        tmem_ld_wait();
+      for (int b = 0; b < 4; ++b) {
+        if (2 * b < n16) {
+          tmem_ld_wait();
+          if (2 * (b + 1) < n16) load_batch(b + 1);
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float p0 = g * 16 + j < wl ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mscaled)) : 0.f;
-          const float p1 = g * 16 + j + 1 < wl ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mscaled)) : 0.f;
-          sum += p0 + p1;
-          pk[j >> 1] = pack_bf16x2(p0, p1);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int g = 2 * b + hh;
+            const uint32_t* v = buf[b & 1] + hh * 16;
+            if (g < n16 - 1) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[j]));
+                mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
+              }
+            } else if (g == n16 - 1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) mx0 = fmaxf(mx0, j < tail ? __uint_as_float(v[j]) : -INFINITY);
+            }
+          }
         }
-        // P columns [8g, 8g+8) overwrite S columns that this thread has already consumed (8g + 8 <= 16 (g + 1))
-        tmem_st8(t_s + g * 8, pk);
       }
+      // p = exp2((s - max) * scale), row sum in fp32, bf16 pairs back into the slot's first columns
+      const float mscaled = fmaxf(mx0, mx1) * scale_log2e;
+      float sum0 = 0.f, sum1 = 0.f;
+      load_batch(0);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (2 * b < n16) {
+          tmem_ld_wait();
+          if (2 * (b + 1) < n16) load_batch(b + 1);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int g = 2 * b + hh;
+            if (g < n16) {
+              const uint32_t* v = buf[b & 1] + hh * 16;
+              uint32_t pk[8];
+              if (g < n16 - 1) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mscaled));
+                  const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mscaled));
+                  sum0 += p0;
+                  sum1 += p1;
+                  pk[j >> 1] = pack_bf16x2(p0, p1);
+                }
+              } else {  // the window's last granule: keys at or beyond `tail` get p = 0 (select, so NaN / Inf scores cannot leak)
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mscaled));
+                  const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mscaled));
+                  const float p0 = j < tail ? e0 : 0.f, p1 = j + 1 < tail ? e1 : 0.f;
+                  sum0 += p0;
+                  sum1 += p1;
+                  pk[j >> 1] = pack_bf16x2(p0, p1);
+                }
+              }
+              // P columns [8g, 8g+8), g <= 2b+1, end at 16b+16 <= 32(b+1): below every S column still to be read or in flight
+              tmem_st8(t_s + g * 8, pk);
+            }
+          }
+        }
+      }
+      const float sum = sum0 + sum1;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -220,28 +276,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       tc_fence_after();
       const float inv = 1.0f / sum;
       __nv_bfloat16* orow = out + (static_cast<long long>(wd.x) + row) * d + h * AT_HD;
+      uint32_t o[AT_HD];
 #pragma unroll
-      for (int g = 0; g < AT_HD / 16; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_s + 128 + g * 16, v);
-        tmem_ld_wait();
-        if (row < wl) {
-          uint4 a, b;
-          a.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-          a.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-          a.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-          a.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-          b.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
-          b.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
-          b.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
-          b.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
-          reinterpret_cast<uint4*>(orow + g * 16)[0] = a;
-          reinterpret_cast<uint4*>(orow + g * 16)[1] = b;
+      for (int g = 0; g < AT_HD / 16; ++g) tmem_ld16(t_s + 128 + g * 16, o + g * 16);
+      tmem_ld_wait();
+      if (row < wl) {
+#pragma unroll
+        for (int g = 0; g < AT_HD / 8; ++g) {
+          uint4 a;
+          a.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+          a.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+          a.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+          a.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+          reinterpret_cast<uint4*>(orow)[g] = a;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&slot_empty[wg]);
+      if (lane == 0) mbar_arrive(&o_empty[wg]);
     }
   }
 
@@ -255,16 +307,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
 
 }  // namespace
 
-// tm_qkv: make_tmap_rowmajor over the packed qkv activation [tokens, 3 d] with box rows = 128
+// tm_qkv: make_tmap_rowmajor over the head-major qkv activation viewed as [3 * heads * head_rows, 64], box rows = 128
 cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len, int d,
-                                       int heads, int num_sms, cudaStream_t stream) {
+                                       int heads, int head_rows, int num_sms, cudaStream_t stream) {
   if (n_win == 0) return cudaSuccess;
   if (d != heads * AT_HD || max_win_len > AT_ROWS) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   if (e != cudaSuccess) return e;
   const float scale_log2e = 0.125f * 1.44269504088896340736f;  // head_dim^-0.5 * log2(e)
   const int grid = std::min(n_win * heads, num_sms);
-  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, out, scale_log2e);
+  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, head_rows, out, scale_log2e);
   return cudaGetLastError();
 }
 

@@ -230,7 +230,8 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 
 __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                           __nv_bfloat16* __restrict__ out,
-                                                                          const int2* __restrict__ win, int d, float scale_log2e) {
+                                                                          const int2* __restrict__ win, int d, int heads, long long head_rows,
+                                                                          float scale_log2e) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int2 wd = win[blockIdx.x];
   const int start = wd.x, wl = wd.y;
@@ -240,17 +241,19 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
   __nv_bfloat16* sV = sK + wl16 * KV_STRIDE;
   __nv_bfloat16* sQ = sV + wl16 * KV_STRIDE;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long ldq = 3LL * d;
-  const __nv_bfloat16* base = qkv + static_cast<long long>(start) * ldq + head * HD;
+  // head-major qkv: plane (section, head) = [head_rows tokens][64]
+  const __nv_bfloat16* qb = qkv + (static_cast<long long>(head) * head_rows + start) * HD;
+  const __nv_bfloat16* kb = qkv + (static_cast<long long>(heads + head) * head_rows + start) * HD;
+  const __nv_bfloat16* vb = qkv + (static_cast<long long>(2 * heads + head) * head_rows + start) * HD;
 
   // stage Q, K, V with 16-byte loads, 128 contiguous bytes per row (rows >= wl zero-filled so masked P = 0 never meets garbage)
   for (int i = tid; i < wl16 * 8; i += ATT_WARPS * 32) {
     const int r = i >> 3, c = (i & 7) * 8;
     uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
     if (r < wl) {
-      q = *reinterpret_cast<const uint4*>(base + r * ldq + c);
-      k = *reinterpret_cast<const uint4*>(base + r * ldq + d + c);
-      v = *reinterpret_cast<const uint4*>(base + r * ldq + 2 * d + c);
+      q = *reinterpret_cast<const uint4*>(qb + r * HD + c);
+      k = *reinterpret_cast<const uint4*>(kb + r * HD + c);
+      v = *reinterpret_cast<const uint4*>(vb + r * HD + c);
     }
     *reinterpret_cast<uint4*>(sQ + r * KV_STRIDE + c) = q;
     *reinterpret_cast<uint4*>(sK + r * KV_STRIDE + c) = k;
@@ -396,7 +399,7 @@ cudaError_t launch_layernorm_fp8(const __nv_bfloat16* x, const float* gamma, con
 }
 
 cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len, int d,
-                                    int heads, cudaStream_t stream) {
+                                    int heads, int head_rows, cudaStream_t stream) {
   if (n_win == 0) return cudaSuccess;
   if (d != heads * HD) return cudaErrorInvalidValue;
   const int wl16 = (max_win_len + 15) & ~15;
@@ -406,7 +409,7 @@ cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out
   if (e != cudaSuccess) return e;
   const float scale_log2e = 0.125f * 1.44269504088896340736f;  // head_dim^-0.5 * log2(e)
   dim3 grid(n_win, heads);
-  window_attention_kernel<<<grid, ATT_WARPS * 32, smem, stream>>>(qkv, out, win, d, scale_log2e);
+  window_attention_kernel<<<grid, ATT_WARPS * 32, smem, stream>>>(qkv, out, win, d, heads, head_rows, scale_log2e);
   return cudaGetLastError();
 }
 

@@ -94,6 +94,17 @@ struct EpiLinear {
   }
 };
 
+// The fused q|k|v projection writes HEAD-MAJOR: out[(section * heads + head) * head_rows + token][64], section = q, k, v.
+// A 64-column group of the [tokens, 3d] product is one head's 128-byte row, so the stores are the same full-line segments
+// as in the row-major layout, but a (window, head) tile of the attention kernel becomes ONE contiguous block of
+// tokens x 128 bytes instead of 128-byte pieces 6 KB apart.
+struct EpiQkv : EpiLinear<ACT_NONE, false> {
+  long long head_rows;  // token capacity of one (section, head) plane
+  __device__ __forceinline__ long long offset(int m, int n) const {
+    return (m < m_valid && n < n_valid) ? (static_cast<long long>(n >> 6) * head_rows + m) * 64 + (n & 63) : -1;
+  }
+};
+
 // FP8 (e4m3 x e4m3) variants: the fp32 accumulator is first dequantised with the dynamic activation scale of its row
 // and the weight scale of its column -- y = acc * sa[m] * sw[n] + bias, what torch._scaled_mm computes for torchao's
 // Float8DynamicActivationFloat8WeightConfig (reference src/server.py:362-371) -- then follows the bf16 epilogue unchanged.

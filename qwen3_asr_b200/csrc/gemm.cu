@@ -137,11 +137,10 @@ cudaError_t linear_dispatch(const LinearArgs& a, const Epi& epi, bool simt, int 
   }
 }
 
-template <int ACT, bool RES>
-cudaError_t linear_kind(const LinearArgs& a, const __nv_bfloat16* residual, bool simt, int num_sms, cudaStream_t stream) {
-  EpiLinear<ACT, RES> e{a.out, a.bias, residual, a.ldo, a.m, a.n};
+template <class Epi>
+cudaError_t linear_kind(const LinearArgs& a, const Epi& e, bool simt, int num_sms, cudaStream_t stream) {
   if (a.fp8) {
-    Scaled<EpiLinear<ACT, RES>> se{e, a.row_scale, a.col_scale};
+    Scaled<Epi> se{e, a.row_scale, a.col_scale};
     return linear_dispatch<tc::K_E4M3>(a, se, simt, num_sms, stream);
   }
   return linear_dispatch<tc::K_BF16>(a, e, simt, num_sms, stream);
@@ -155,9 +154,14 @@ cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_
   if (a.k % kb != 0 || a.n % 16 != 0 || (!simt && (a.bn == 0 || a.n % a.bn != 0))) return cudaErrorInvalidValue;
   if (a.fp8 && (a.row_scale == nullptr || a.col_scale == nullptr)) return cudaErrorInvalidValue;
   switch (a.epi) {
-    case LIN_PLAIN: return linear_kind<ACT_NONE, false>(a, nullptr, simt, num_sms, stream);
-    case LIN_GELU: return linear_kind<ACT_GELU, false>(a, nullptr, simt, num_sms, stream);
-    case LIN_RESIDUAL: return linear_kind<ACT_NONE, true>(a, a.residual, simt, num_sms, stream);
+    case LIN_PLAIN: return linear_kind(a, EpiLinear<ACT_NONE, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
+    case LIN_GELU: return linear_kind(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
+    case LIN_RESIDUAL: return linear_kind(a, EpiLinear<ACT_NONE, true>{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, simt, num_sms, stream);
+    case LIN_QKV: {
+      if (a.n % 64 != 0 || a.head_rows < a.m) return cudaErrorInvalidValue;
+      EpiQkv e{{a.out, a.bias, nullptr, 0, a.m, a.n}, a.head_rows};
+      return linear_kind(a, e, simt, num_sms, stream);
+    }
     default: return cudaErrorInvalidValue;
   }
 }

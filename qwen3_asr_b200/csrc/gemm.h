@@ -23,7 +23,7 @@ int make_tmap_conv(CUtensorMap* tm, const void* base, long long g_in, int h_in, 
 // Largest supported N tile (256 / 128 / 64) that divides n; 0 if none.
 int pick_bn(int n);
 
-enum LinearEpi : int { LIN_PLAIN = 0, LIN_GELU = 1, LIN_RESIDUAL = 2 };
+enum LinearEpi : int { LIN_PLAIN = 0, LIN_GELU = 1, LIN_RESIDUAL = 2, LIN_QKV = 3 /* head-major output, see EpiQkv */ };
 
 struct LinearArgs {
   const CUtensorMap* tm_a;     // [m_cap, k] activations
@@ -39,6 +39,7 @@ struct LinearArgs {
   long long ldo;
   const float* bias;           // [n] or nullptr
   const __nv_bfloat16* residual;  // LIN_RESIDUAL: [m, ldo]
+  long long head_rows;         // LIN_QKV: token capacity of one (section, head) plane of the head-major output
   // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,
   // y = acc * row_scale[m] * col_scale[n] + bias
   int fp8;

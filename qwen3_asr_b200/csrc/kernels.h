@@ -50,12 +50,14 @@ cudaError_t launch_layernorm_fp8(const __nv_bfloat16* x, const float* gamma, con
                                  int rows, int d, float eps, cudaStream_t stream);
 
 // ---- windowed attention ----------------------------------------------------------------------
-// qkv: [tokens, 3d] (q | k | v, head h at columns h*64); out: [tokens, d]; win: [n_win] (start, len)
+// qkv: head-major [3 (q, k, v)][heads][head_rows tokens][64] (written by the QKV GEMM's EpiQkv epilogue); out: [tokens, d];
+// win: [n_win] (start, len)
 cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* win, int n_win,
-                                    int max_win_len, int d, int heads, cudaStream_t stream);
+                                    int max_win_len, int d, int heads, int head_rows, cudaStream_t stream);
 
-// tcgen05 version (attention_tc.cu): windows up to 128 tokens; tm_qkv = 128B-swizzled map over qkv [tokens, 3d], box 64 x 128
+// tcgen05 version (attention_tc.cu): windows up to 128 tokens; tm_qkv = 128B-swizzled map over the same buffer viewed as
+// [3 * heads * head_rows, 64], box 64 x 128
 cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len,
-                                       int d, int heads, int num_sms, cudaStream_t stream);
+                                       int d, int heads, int head_rows, int num_sms, cudaStream_t stream);
 
 }  // namespace qasr

@@ -103,6 +103,7 @@ struct qasr_handle_s {
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
   int chunks_per_window = 8;
   int max_chunks = 0, max_tokens = 0;
+  int head_rows = 0;        // token capacity of one (section, head) plane of the head-major qkv buffer
 
   std::map<std::string, HostTensor> staged;
   std::vector<void*> allocs;
@@ -426,6 +427,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     LinearArgs la{};
     la.tm_a = tm_a; la.tm_b = &w.tm; la.bn = w.bn; la.a = a_raw; la.lda = w.k; la.b = w.w; la.ldb = w.k;
     la.m = ntok; la.n = w.n; la.k = w.k; la.epi = epi; la.out = o; la.ldo = ldo; la.bias = w.b; la.residual = residual;
+    la.head_rows = h->head_rows;
     if (h->fp8) {
       if (a_raw != nullptr) QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(a_raw, ntok, w.k));
       la.tm_a = w.k == d ? &h->tm_a8_d : &h->tm_a8_ffn;
@@ -449,13 +451,13 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   for (const LayerW& L : h->layers) {
     const double tk = 2.0 * ntok;
     if ((rc = layernorm(L.ln1_g, L.ln1_b)) != 0) return rc;
-    if ((rc = linear("qkv_gemm", tk * 3 * d * d, &h->tm_h, ln_out, L.qkv, LIN_PLAIN, h->qkv, 3LL * d, nullptr)) != 0) return rc;
+    if ((rc = linear("qkv_gemm", tk * 3 * d * d, &h->tm_h, ln_out, L.qkv, LIN_QKV, h->qkv, 0, nullptr)) != 0) return rc;
     if (mb.max_win <= 128 && !h->attn_simt)
       QASR_LAUNCH(h, "window_attention", att_flops, stream,
-                  launch_window_attention_tc(&h->tm_qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, h->num_sms, stream));
+                  launch_window_attention_tc(&h->tm_qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, h->head_rows, h->num_sms, stream));
     else
       QASR_LAUNCH(h, "window_attention", att_flops, stream,
-                  launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, stream));
+                  launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, h->head_rows, stream));
     if ((rc = linear("out_proj_gemm", tk * d * d, &h->tm_att, h->att, L.out, LIN_RESIDUAL, h->x, d, h->x)) != 0) return rc;
     if ((rc = layernorm(L.ln2_g, L.ln2_b)) != 0) return rc;
     if ((rc = linear("fc1_gemm", tk * d * c.encoder_ffn_dim, &h->tm_h, ln_out, L.fc1, LIN_GELU, h->ffn, c.encoder_ffn_dim, nullptr)) != 0) return rc;
@@ -698,7 +700,9 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = make_tmap_rowmajor(&h->tm_h, h->hbuf, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_att, h->att, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_ffn, h->ffn, mt, ffn, ffn, 128)) != 0) return rc;
-  if ((rc = make_tmap_rowmajor(&h->tm_qkv, h->qkv, mt, 3LL * d, 3LL * d, 128)) != 0) return rc;
+  // head-major qkv (EpiQkv): [3][heads][mt][64] viewed as a [3 * heads * mt, 64] matrix for the attention kernel's TMA
+  h->head_rows = static_cast<int>(mt);
+  if ((rc = make_tmap_rowmajor(&h->tm_qkv, h->qkv, 3LL * c.encoder_attention_heads * static_cast<long long>(mt), 64, 64, 128)) != 0) return rc;
   // the tcgen05 attention multiplies V rows past a window's end by exact zeros: they must never hold NaN / Inf bit patterns
   QASR_CUDA_CHECK(cudaMemset(h->qkv, 0, mt * 3 * d * sizeof(bf16)));
   if (h->fp8) {
@@ -1169,47 +1173,61 @@ int qasr_debug_layernorm(const void* x, const float* gamma, const float* beta, v
   return 0;
 }
 
-int qasr_debug_attention_tc(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int tokens, int d, int heads,
-                            void* stream_v) {
-  QASR_REQUIRE(qkv != nullptr && out != nullptr && win_start_len_host != nullptr && n_win > 0 && tokens > 0, "qasr_debug_attention_tc: bad argument");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  CUtensorMap tm;
-  int rc;
-  if ((rc = make_tmap_rowmajor(&tm, qkv, tokens, 3LL * d, 3LL * d, 128)) != 0) return rc;
-  int dev = 0, sms = kNumSMs;
-  QASR_CUDA_CHECK(cudaGetDevice(&dev));
-  QASR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+namespace {
+// tests hand in the natural [tokens, 3d] layout; the kernels read the head-major one the QKV GEMM writes
+int debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int tokens, int d, int heads, bool tc,
+                    cudaStream_t stream) {
+  QASR_REQUIRE(qkv != nullptr && out != nullptr && win_start_len_host != nullptr && n_win > 0 && tokens > 0 && d == heads * 64,
+               "qasr_debug_attention: bad argument");
+  const int head_rows = static_cast<int>(align_up(static_cast<size_t>(tokens), 128));
+  const size_t plane = static_cast<size_t>(head_rows) * 64;
+  bf16* hm = nullptr;
   int2* dwin = nullptr;
-  QASR_CUDA_CHECK(cudaMalloc(&dwin, n_win * sizeof(int2)));
+  QASR_CUDA_CHECK(cudaMalloc(&hm, 3 * heads * plane * sizeof(bf16)));
+  cudaError_t e = cudaMalloc(&dwin, n_win * sizeof(int2));
+  if (e == cudaSuccess) e = cudaMemsetAsync(hm, 0, 3 * heads * plane * sizeof(bf16), stream);
+  for (int sec = 0; sec < 3 && e == cudaSuccess; ++sec)
+    for (int hd = 0; hd < heads && e == cudaSuccess; ++hd)
+      e = cudaMemcpy2DAsync(hm + (static_cast<size_t>(sec) * heads + hd) * plane, 64 * sizeof(bf16),
+                            static_cast<const bf16*>(qkv) + static_cast<size_t>(sec) * d + hd * 64, 3 * static_cast<size_t>(d) * sizeof(bf16),
+                            64 * sizeof(bf16), tokens, cudaMemcpyDeviceToDevice, stream);
   int max_win = 0;
   for (int i = 0; i < n_win; ++i) max_win = std::max(max_win, win_start_len_host[2 * i + 1]);
-  cudaError_t e = cudaMemcpyAsync(dwin, win_start_len_host, n_win * sizeof(int2), cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = launch_window_attention_tc(&tm, static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, sms, stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  cudaFree(dwin);
-  if (e != cudaSuccess) {
-    set_last_error(std::string("qasr_debug_attention_tc: ") + cudaGetErrorString(e));
-    return 2;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dwin, win_start_len_host, n_win * sizeof(int2), cudaMemcpyHostToDevice, stream);
+  int rc = 0;
+  if (e == cudaSuccess) {
+    if (tc) {
+      CUtensorMap tm;
+      rc = make_tmap_rowmajor(&tm, hm, 3LL * heads * head_rows, 64, 64, 128);
+      int dev = 0, sms = kNumSMs;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (rc == 0) e = launch_window_attention_tc(&tm, static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, head_rows, sms, stream);
+    } else {
+      e = launch_window_attention(hm, static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, head_rows, stream);
+    }
   }
-  return 0;
-}
-
-int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream_v) {
-  QASR_REQUIRE(qkv != nullptr && out != nullptr && win_start_len_host != nullptr && n_win > 0, "qasr_debug_attention: bad argument");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  int2* dwin = nullptr;
-  QASR_CUDA_CHECK(cudaMalloc(&dwin, n_win * sizeof(int2)));
-  int max_win = 0;
-  for (int i = 0; i < n_win; ++i) max_win = std::max(max_win, win_start_len_host[2 * i + 1]);
-  cudaError_t e = cudaMemcpyAsync(dwin, win_start_len_host, n_win * sizeof(int2), cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = launch_window_attention(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   cudaFree(dwin);
+  cudaFree(hm);
   if (e != cudaSuccess) {
     set_last_error(std::string("qasr_debug_attention: ") + cudaGetErrorString(e));
     return 2;
   }
-  return 0;
+  return rc;
+}
+}  // namespace
+
+int qasr_debug_attention_tc(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int tokens, int d, int heads,
+                            void* stream_v) {
+  return debug_attention(qkv, out, win_start_len_host, n_win, tokens, d, heads, true, static_cast<cudaStream_t>(stream_v));
+}
+
+int qasr_debug_attention(const void* qkv, void* out, const int32_t* win_start_len_host, int n_win, int d, int heads, void* stream_v) {
+  int tokens = 0;
+  if (win_start_len_host != nullptr)
+    for (int i = 0; i < n_win; ++i) tokens = std::max(tokens, win_start_len_host[2 * i] + win_start_len_host[2 * i + 1]);
+  return debug_attention(qkv, out, win_start_len_host, n_win, tokens, d, heads, false, static_cast<cudaStream_t>(stream_v));
 }
 
 }  // extern "C"
