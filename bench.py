@@ -27,6 +27,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM traffic measured once with ncu --set full (profiles/): the bench itself never runs under a profiler
+NCU_GEMM_DRAM_BYTES_PER_STEP = (3.075055 + 0.720616 + 0.772438 + 0.174890 + 0.230114 + 0.014834 + 24 * (
+    0.032015 + 0.022830 + 0.053376 + 0.000166 + 0.034131 + 0.047290 + 0.136851 + 0.009352)) * 1e9
+NCU_MEL_DRAM_BYTES_PER_LAUNCH = (497.989120 + 389.929216) * 1e6
+
 METRIC = "audio-sec encoded/sec (mel+encoder, 1.7B)"
 UNIT = "audio-s/s"
 MODEL = "1.7B"
@@ -323,7 +328,10 @@ def main():
             "algorithmic_flops_per_step": gemm_flops / args.steps, "launches_per_step": gemm_launches / args.steps,
             "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
             "timing": "per-launch CUDA events on the launching stream over a second pass of the same K steps",
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the family's 101 launches of one step (conv2 3.80 GB, conv3 0.95 GB,
+            # conv_out 0.24 GB, per layer qkv 55 MB + out_proj 54 MB + fc1 81 MB + fc2 146 MB), ncu --set full, divided by 101
+            "traffic": NCU_GEMM_DRAM_BYTES_PER_STEP / 101.0,
+            "traffic_source": "profiles/r01d_gemm_raw_summary.txt (one ncu --set full capture of each kernel of the family, C2 batch)",
         }
         kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                        "tflops": (v["work"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and k != "logmel" and v["work"] > 0 else None}
@@ -336,7 +344,9 @@ def main():
             roofline_mel = {"bound": "hbm", "kernel": "logmel_kernel (persistent, ticketed frame + clamp items)", "achieved": gbs, "peak": peaks["hbm_gbs"],
                             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
                             "algorithmic_bytes_per_launch": m["work"] / m["launches"], "avg_launch_ms": (m["ms"] + fin["ms"]) / m["launches"],
-                            "workload": "8 x C2 batch (256 x 30 s): 491 MB PCM in, 393 MB log-mel out, >> L2", "traffic": None,
+                            "workload": "8 x C2 batch (256 x 30 s): 491 MB PCM in, 393 MB log-mel out, >> L2",
+                            # dram__bytes_read.sum 498.0 MB + dram__bytes_write.sum 389.9 MB of one launch on this workload
+                            "traffic": NCU_MEL_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01c_mel_ticketed_summary.txt",
                             "audio_s_per_s": 8 * audio_s_per_step * m["launches"] / ((m["ms"] + fin["ms"]) / 1e3)}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
