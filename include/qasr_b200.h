@@ -143,6 +143,37 @@ QASR_API int qasr_wait(qasr_handle_t h, uint64_t ticket);
 QASR_API int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
                      int64_t* feature_lens_out, void* stream);
 
+/* ---- WebSocket pre-frontend: the per-window CPU passes of the reference's
+ * WS path, batched over streams on the device.  Streams are packed back to back; offsets are HOST int64 [n_streams + 1]. */
+
+/* Output length of qasr_resample_pcm16 for an input of n_in samples: ceil(n_in * up / down). */
+QASR_API int64_t qasr_resample_len(int64_t n_in, int up, int down);
+
+/* int16 -> resample by up/down -> int16 (replaces _resample_pcm_bytes, src/server.py:32-42: astype(float32) ->
+ * librosa.resample -> astype(int16), i.e. truncation toward zero; this library saturates where numpy would wrap).
+ * The resampler is the polyphase Kaiser-windowed sinc of scipy.signal.resample_poly (librosa's soxr_hq is not
+ * reproducible offline: parity unpinned against the reference, pinned against scipy), evaluated in float64.
+ *   taps               host float64 [n_taps], n_taps odd, already scaled by `up` (scipy: firwin(...) * up), or NULL for
+ *                      the built-in design firwin(20 * max(up, down) + 1, 1 / max(up, down), ("kaiser", 5.0)) * up
+ *   out_dev            int16, stream i at [out_offsets_out[i], out_offsets_out[i + 1]); out_capacity in samples
+ *   out_offsets_out    host int64 [n_streams + 1], written by the call */
+QASR_API int qasr_resample_pcm16(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_offsets, int n_streams, int up, int down,
+                                 const double* taps, int n_taps, int16_t* out_dev, int64_t out_capacity, int64_t* out_offsets_out,
+                                 void* stream);
+
+/* One WS window per stream: int16 16 kHz samples (+ pad_samples[i] int16 zeros appended: the 600 ms flush silence)
+ * -> float32 / 32768 -> SOS band-pass in float64, zero initial state, cast to float32 -> zero-padded to min_samples
+ * (replaces _transcribe_with_context's numpy prologue, src/server.py:1321-1338, and _telephony_bandpass, :26-29 =
+ * scipy.signal.sosfilt(butter(4, [300, 3400], "bandpass", fs=16000, output="sos"), audio).astype(float32)).
+ *   pad_samples        host int32 [n_streams] or NULL
+ *   sos                host float64 [n_sections, 6] in scipy's layout (b0 b1 b2 a0 a1 a2), n_sections <= 8; NULL / 0 = no filter
+ *   min_samples        shorter windows are zero-padded to this length AFTER filtering (the SDK's 0.5 s minimum); 0 = off
+ *   out_dev            float32, stream i at [out_offsets_out[i], out_offsets_out[i + 1]) -- directly usable as the
+ *                      pcm_dev / clip_offsets of qasr_logmel and qasr_encode_pcm; out_capacity in samples */
+QASR_API int qasr_ws_window(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_offsets, int n_streams, const int32_t* pad_samples,
+                            const double* sos, int n_sections, int min_samples, float* out_dev, int64_t out_capacity,
+                            int64_t* out_offsets_out, void* stream);
+
 QASR_API void qasr_destroy(qasr_handle_t h);
 
 /* ---- launch accounting and per-launch timing (measurement; bench.py's roofline figures) ------- */

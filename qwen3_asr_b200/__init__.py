@@ -8,4 +8,6 @@ the ONNX_ENCODER_PATH / TRT_ENCODER_PATH slots).  Hand-written CUDA behind a C A
 from ._lib import QasrError, load_library  # noqa: F401
 from .encoder import B200AudioEncoder, EncoderOutput, make_config, sinusoid_table  # noqa: F401
 
-__all__ = ["B200AudioEncoder", "EncoderOutput", "QasrError", "load_library", "make_config", "sinusoid_table"]
+from .prefrontend import B200PreFrontend  # noqa: F401
+
+__all__ = ["B200AudioEncoder", "B200PreFrontend", "EncoderOutput", "QasrError", "load_library", "make_config", "sinusoid_table"]

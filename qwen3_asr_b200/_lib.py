@@ -49,6 +49,10 @@ SIGNATURES = {
     "qasr_submit_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P, C.POINTER(C.c_uint64)]),
     "qasr_wait": (C.c_int, [_P, C.c_uint64]),
     "qasr_logmel_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, _I64P, _P]),
+    "qasr_resample_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "qasr_resample_pcm16": (C.c_int, [_P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, _P, C.c_int64, _I64P, _P]),
+    "qasr_ws_window": (C.c_int, [_P, _P, _I64P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_int, _P, C.c_int64,
+                                 _I64P, _P]),
     "qasr_destroy": (None, [_P]),
     "qasr_launch_count": (C.c_uint64, [_P]),
     "qasr_profile_enable": (C.c_int, [_P, C.c_int]),

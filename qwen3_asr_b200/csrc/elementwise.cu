@@ -17,9 +17,10 @@ namespace {
 // implicit-GEMM conv2 reads as padding, col 1 + w holds output column w.  One CTA = one chunk x 13
 // output-column slots; one thread = two adjacent channels (bf16x2 stores, 128 B per warp).
 // ---------------------------------------------------------------------------------------------
-constexpr int C1_COLS = 13;                    // column slots per CTA (52 / 4)
-constexpr int C1_TILE_W = 2 * C1_COLS + 1;     // mel frames needed: 27
+constexpr int C1_COLS = 26;                    // column slots per CTA (52 / 2)
+constexpr int C1_TILE_W = 2 * C1_COLS + 2;     // mel frames needed: 53, padded to an even count (LDS.128 alignment)
 constexpr int C1_TILE_H = 130;                 // mel bins -1 .. 128
+constexpr int C1_THREADS = 480;                // 240 channel pairs x 2 column halves: 15 full warps
 
 template <typename MelT>
 __device__ __forceinline__ float mel_load(const MelT* p);
@@ -28,11 +29,53 @@ __device__ __forceinline__ float mel_load<float>(const float* p) { return bf16_r
 template <>
 __device__ __forceinline__ float mel_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
+// Packed fp32 pairs (FFMA2 / FMUL2, sm_100): one issue slot per two lanes of work.  The kernel is issue-bound, so
+// the channel pair a thread owns rides in one 64-bit register pair through the 9 taps and the GELU polynomial.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 upk(f32x2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf (common.cuh) on a pair: identical operation order per lane, so the results are bit-identical to the scalar form.
+__device__ __forceinline__ f32x2_t gelu_erf2(float xa, float xb) {
+  const float aa = fabsf(xa), ab = fabsf(xb);
+  const f32x2_t a = pk(aa, ab);
+  const float2 u = upk(fma2(pk(0.231641888f, 0.231641888f), a, pk(1.0f, 1.0f)));
+  const f32x2_t t = pk(rcp_approx(u.x), rcp_approx(u.y));
+  f32x2_t p = fma2(pk(0.5307027145f, 0.5307027145f), t, pk(-0.7265760135f, -0.7265760135f));
+  p = fma2(p, t, pk(0.7107068705f, 0.7107068705f));
+  p = fma2(p, t, pk(-0.142248368f, -0.142248368f));
+  p = fma2(p, t, pk(0.127414796f, 0.127414796f));
+  const float2 s = upk(mul2(mul2(a, a), pk(-0.72134752044f, -0.72134752044f)));
+  const f32x2_t e = pk(ex2_approx(s.x), ex2_approx(s.y));
+  const f32x2_t q = mul2(mul2(p, t), e);
+  return fma2(pk(-aa, -ab), q, pk(fmaxf(xa, 0.f), fmaxf(xb, 0.f)));
+}
+
 template <typename MelT>
-__global__ void __launch_bounds__(256) conv1_kernel(const MelT* __restrict__ mel, long long ld, const ChunkDesc* __restrict__ chunks,
-                                                    const float* __restrict__ w, const float* __restrict__ bias, int channels,
-                                                    __nv_bfloat16* __restrict__ act1) {
-  __shared__ float tile[C1_TILE_H][C1_TILE_W + 1];
+__global__ void __launch_bounds__(C1_THREADS, 2) conv1_kernel(const MelT* __restrict__ mel, long long ld, const ChunkDesc* __restrict__ chunks,
+                                                              const float* __restrict__ w, const float* __restrict__ bias, int channels,
+                                                              __nv_bfloat16* __restrict__ act1) {
+  // every mel value twice, {x, x}: one LDS.64 / LDS.128 hands FFMA2 its broadcast operand without a register move
+  extern __shared__ __align__(16) uint8_t c1_smem[];
+  float2 (*tile)[C1_TILE_W] = reinterpret_cast<float2 (*)[C1_TILE_W]>(c1_smem);
   const int chunk = blockIdx.x;
   const int slot0 = blockIdx.y * C1_COLS;  // first column slot (0..51) of this CTA
   const ChunkDesc cd = chunks[chunk];
@@ -40,23 +83,24 @@ __global__ void __launch_bounds__(256) conv1_kernel(const MelT* __restrict__ mel
 
   // mel frames f = 2*(slot-1) - 1 + j for the slots of this CTA: f0 = 2*slot0 - 3
   const int f0 = 2 * slot0 - 3;
-  for (int i = tid; i < C1_TILE_H * C1_TILE_W; i += 256) {
+  for (int i = tid; i < C1_TILE_H * C1_TILE_W; i += C1_THREADS) {
     const int r = i / C1_TILE_W, cc = i - r * C1_TILE_W;
     const int bin = r - 1, f = f0 + cc;
     float v = 0.f;
     if (bin >= 0 && bin < 128 && f >= 0 && f < cd.valid) v = mel_load<MelT>(mel + bin * ld + cd.mel_col0 + f);
-    tile[r][cc] = v;
+    tile[r][cc] = make_float2(v, v);
   }
   __syncthreads();
 
-  const int c0 = 2 * tid;
+  const int pair = tid % 240, half = tid / 240;
+  const int c0 = 2 * pair;
   if (c0 >= channels) return;
-  float wa[9], wb[9];
+  f32x2_t wv[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) { wa[t] = w[c0 * 9 + t]; wb[t] = w[(c0 + 1) * 9 + t]; }
-  const float ba = bias[c0], bb = bias[c0 + 1];
+  for (int t = 0; t < 9; ++t) wv[t] = pk(w[c0 * 9 + t], w[(c0 + 1) * 9 + t]);
+  const f32x2_t bv = pk(bias[c0], bias[c0 + 1]);
 
-  for (int s = 0; s < C1_COLS; ++s) {
+  for (int s = half * (C1_COLS / 2); s < (half + 1) * (C1_COLS / 2); ++s) {
     const int slot = slot0 + s;
     const int ow = slot - 1;  // output column of the chunk; slot 0 / 51 are padding
     const bool live = ow >= 0 && ow < cd.w1;
@@ -65,21 +109,23 @@ __global__ void __launch_bounds__(256) conv1_kernel(const MelT* __restrict__ mel
       for (int h = 0; h < ACT1_H; ++h) *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(h) * channels) = 0u;
       continue;
     }
-    const int cc = 2 * s;  // tile column of frame 2*ow - 1
-#pragma unroll 4
+    const int cc = 2 * s;  // tile column of frame 2*ow - 1 (even: the {x0,x0,x1,x1} quad is 16-byte aligned)
+#pragma unroll 2
     for (int h = 0; h < ACT1_H; ++h) {
-      float xa = ba, xb = bb;
+      f32x2_t acc = bv;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float x = tile[2 * h + kh][cc + kw];
-          xa = fmaf(wa[kh * 3 + kw], x, xa);
-          xb = fmaf(wb[kh * 3 + kw], x, xb);
-        }
-      const float2 xr = bf16_round2(xa, xb);
-      const float ya = gelu_erf(xr.x), yb = gelu_erf(xr.y);
-      *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(h) * channels) = pack_bf16x2(ya, yb);
+      for (int kh = 0; kh < 3; ++kh) {
+        const float2* row = &tile[2 * h + kh][cc];
+        const ulonglong2 x01 = *reinterpret_cast<const ulonglong2*>(row);
+        const f32x2_t x2 = *reinterpret_cast<const f32x2_t*>(row + 2);
+        acc = fma2(wv[kh * 3 + 0], x01.x, acc);
+        acc = fma2(wv[kh * 3 + 1], x01.y, acc);
+        acc = fma2(wv[kh * 3 + 2], x2, acc);
+      }
+      const float2 a = upk(acc);
+      const float2 xr = bf16_round2(a.x, a.y);
+      const float2 y = upk(gelu_erf2(xr.x, xr.y));
+      *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(h) * channels) = pack_bf16x2(y.x, y.y);
     }
   }
 }
@@ -360,12 +406,16 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
 cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, const ChunkDesc* chunks, int n_chunks, const float* w,
                          const float* bias, int channels, __nv_bfloat16* act1, cudaStream_t stream) {
   if (n_chunks == 0) return cudaSuccess;
-  if (channels > 512 || (channels & 1)) return cudaErrorInvalidValue;
+  if (channels > 480 || (channels & 1)) return cudaErrorInvalidValue;
   dim3 grid(n_chunks, ACT1_PITCH / C1_COLS);
+  constexpr int smem = C1_TILE_H * C1_TILE_W * sizeof(float2);
+  cudaError_t e = mel_is_bf16 ? cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                              : cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
   if (mel_is_bf16)
-    conv1_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, channels, act1);
+    conv1_kernel<__nv_bfloat16><<<grid, C1_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, channels, act1);
   else
-    conv1_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, channels, act1);
+    conv1_kernel<float><<<grid, C1_THREADS, smem, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, channels, act1);
   return cudaGetLastError();
 }
 

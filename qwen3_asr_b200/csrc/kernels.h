@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <vector>
 
 #include <cuda.h>
 
@@ -21,6 +22,25 @@ cudaError_t upload_mel_constants(const mel::Tables* host_tables);
 // zeroed by the launcher on `stream`.
 cudaError_t launch_logmel(const float* pcm, const mel::Item* items, int n_items, const mel::Tables* tables, float* mel_out,
                           long long mel_ld, unsigned int* counters, int n_clips, int num_sms, cudaStream_t stream);
+
+// ---- WS pre-frontend (prefrontend.cu) ---------------------------------------------------------
+struct WsStream {       // one WS window
+  long long in_off;     // first int16 sample in the packed input
+  long long in_len;     // int16 samples present
+  long long flt_len;    // in_len + flush silence: the span the band-pass runs over
+  long long out_off;    // first float sample in the packed output
+  long long out_len;    // max(flt_len, minimum clip length): [flt_len, out_len) is zero
+};
+struct RsStream {
+  long long in_off, in_len, out_off, out_len;
+};
+void design_resample_taps(int up, int down, std::vector<double>* taps, int* half_len);
+int sos_warmup(const double* sos, int n_sections);  // < 0: filter not (safely) stable
+cudaError_t launch_ws_window(const int16_t* pcm16, const WsStream* streams_dev, int n_streams, long long max_out_len, const double* sos,
+                             int n_sections, int warm, float* out, cudaStream_t stream);
+cudaError_t launch_resample_pcm16(const int16_t* in, const RsStream* streams_dev, int n_streams, long long max_out_len,
+                                  const double* taps_dev, int n_taps, int half_len, int up, int down, int16_t* out, int num_sms,
+                                  cudaStream_t stream);
 
 // ---- conv1 (elementwise.cu) ------------------------------------------------------------------
 struct ChunkDesc {

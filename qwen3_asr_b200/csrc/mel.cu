@@ -158,15 +158,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // clip-relative sample index of slab position 0
 __device__ __forceinline__ int slab_s0(const Item& it) { return it.frame0 * HOP - N_FFT / 2; }
 
-// One thread: start the bulk copies of an item's slab (34 hop rows of 164 floats from the 16-byte aligned address at or
-// below the row's first sample; stage 1 adds the 0..3 float shift back).
-__device__ __forceinline__ void issue_slab_bulk(MelSmem& sm, const float* __restrict__ pcm, const Item& it) {
+// Warp 0: start the bulk copies of an item's slab (34 hop rows of 164 floats from the 16-byte aligned address at or
+// below the row's first sample; stage 1 adds the 0..3 float shift back).  One row per lane, so the 34 copies leave in two
+// instructions instead of a 34-trip loop on the thread every barrier waits for.  The expect_tx arrival is the phase's only
+// pending arrival, so rows that complete before it is posted cannot flip the phase early.
+__device__ __forceinline__ void issue_slab_bulk(MelSmem& sm, const float* __restrict__ pcm, const Item& it, int lane) {
   const float* src = pcm + it.pcm_off + slab_s0(it);
   src -= (reinterpret_cast<uintptr_t>(src) >> 2) & 3;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the slab vs the async writes
-  mbar_expect_tx(&sm.mbar, SLAB_ROWS * ROW_COPY * 4);
-#pragma unroll 1
-  for (int r = 0; r < SLAB_ROWS; ++r) bulk_g2s(sm.slab + r * SLAB_PITCH, src + r * HOP, ROW_COPY * 4, &sm.mbar);
+  if (lane == 0) mbar_expect_tx(&sm.mbar, SLAB_ROWS * ROW_COPY * 4);
+  for (int r = lane; r < SLAB_ROWS; r += 32) bulk_g2s(sm.slab + r * SLAB_PITCH, src + r * HOP, ROW_COPY * 4, &sm.mbar);
+}
+// warp 0, after lane 0 decided `go`: broadcast it and issue
+__device__ __forceinline__ void warp0_issue(MelSmem& sm, const float* __restrict__ pcm, const Item& it, int go, int lane) {
+  go = __shfl_sync(0xffffffffu, go, 0);
+  __syncwarp();  // lane 0's descriptor (cp.async + wait) is visible to the other lanes
+  if (go) issue_slab_bulk(sm, pcm, it, lane);
 }
 
 __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restrict__ pcm, const Item* __restrict__ items, int n_items,
@@ -198,12 +205,10 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restr
     sm.idx[0] = t0;
     sm.n_deferred = 0;
     sm.run_clamp = 0;
-    if (t0 < n_items) {
-      sm.desc[0] = items[t0];
-      if (sm.desc[0].kind == 0 && sm.desc[0].bulk) issue_slab_bulk(sm, pcm, sm.desc[0]);
-    }
+    if (t0 < n_items) sm.desc[0] = items[t0];
   }
   __syncthreads();
+  if (warp == 0) warp0_issue(sm, pcm, sm.desc[0], lane == 0 && sm.idx[0] < n_items && sm.desc[0].kind == 0 && sm.desc[0].bulk, lane);
   int slot = 0;
   uint32_t parity = 0;
 
@@ -263,10 +268,16 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restr
           sm.deferred[sm.n_deferred++] = it;
           sm.run_clamp = 0;
         }
+      }
+      if (warp == 0) {
         // the slab is idle during a clamp item: start the next item's copy right away
-        cp_async_wait_all();
-        if (t_next < n_items && sm.desc[slot ^ 1].kind == 0 && sm.desc[slot ^ 1].bulk) issue_slab_bulk(sm, pcm, sm.desc[slot ^ 1]);
-        t_next = t_after;
+        int go = 0;
+        if (lane == 0) {
+          cp_async_wait_all();
+          go = t_next < n_items && sm.desc[slot ^ 1].kind == 0 && sm.desc[slot ^ 1].bulk;
+          t_next = t_after;
+        }
+        warp0_issue(sm, pcm, sm.desc[slot ^ 1], go, lane);
       }
       __syncthreads();
       if (sm.run_clamp) clamp_tile(sm.clamp, sm.floor_v);
@@ -323,10 +334,14 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restr
     }
     __syncthreads();  // E complete, slab free
 
-    if (tid == 0) {
-      cp_async_wait_all();
-      if (t_next < n_items && sm.desc[slot ^ 1].kind == 0 && sm.desc[slot ^ 1].bulk) issue_slab_bulk(sm, pcm, sm.desc[slot ^ 1]);
-      t_next = t_after;
+    if (warp == 0) {
+      int go = 0;
+      if (lane == 0) {
+        cp_async_wait_all();
+        go = t_next < n_items && sm.desc[slot ^ 1].kind == 0 && sm.desc[slot ^ 1].bulk;
+        t_next = t_after;
+      }
+      warp0_issue(sm, pcm, sm.desc[slot ^ 1], go, lane);
     }
 
     // ---------------- stage 2: 13 complex 16-point FFTs per frame -> power ----------------

@@ -972,6 +972,111 @@ int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* 
   return qasr_wait(h, ticket);
 }
 
+int64_t qasr_resample_len(int64_t n_in, int up, int down) {
+  if (n_in <= 0 || up <= 0 || down <= 0) return 0;
+  return (n_in * up + down - 1) / down;
+}
+
+int qasr_resample_pcm16(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_offsets, int n_streams, int up, int down,
+                        const double* taps, int n_taps, int16_t* out_dev, int64_t out_capacity, int64_t* out_offsets_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && in_offsets != nullptr && out_offsets_out != nullptr && n_streams >= 0, "qasr_resample_pcm16: bad argument");
+  QASR_REQUIRE(up >= 1 && down >= 1 && up <= 4096 && down <= 4096, "qasr_resample_pcm16: up / down must be in [1, 4096]");
+  QASR_REQUIRE(n_streams <= 65535, "qasr_resample_pcm16: at most 65535 streams per call");
+  QASR_REQUIRE(taps == nullptr || (n_taps >= 1 && (n_taps & 1) == 1), "qasr_resample_pcm16: n_taps must be odd");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  {
+    int a = up, b = down;
+    while (b != 0) { const int t = a % b; a = b; b = t; }
+    QASR_REQUIRE(a == 1, "qasr_resample_pcm16: up / down must be coprime (divide by their gcd, as resample_poly does)");
+  }
+  std::vector<double> designed;
+  int half_len = 0;
+  if (taps == nullptr) {
+    if (up == down) { designed.assign(1, 1.0); half_len = 0; }
+    else design_resample_taps(up, down, &designed, &half_len);
+    taps = designed.data();
+    n_taps = static_cast<int>(designed.size());
+  } else {
+    half_len = (n_taps - 1) / 2;
+  }
+  out_offsets_out[0] = 0;
+  long long max_out = 0;
+  for (int i = 0; i < n_streams; ++i) {
+    const int64_t n = in_offsets[i + 1] - in_offsets[i];
+    QASR_REQUIRE(n >= 0, "qasr_resample_pcm16: offsets must be non-decreasing");
+    const int64_t m = qasr_resample_len(n, up, down);
+    out_offsets_out[i + 1] = out_offsets_out[i] + m;
+    max_out = std::max<long long>(max_out, m);
+  }
+  QASR_REQUIRE(out_offsets_out[n_streams] <= out_capacity, "qasr_resample_pcm16: out_capacity too small");
+  if (n_streams == 0 || max_out == 0) return 0;
+  QASR_REQUIRE(pcm16_dev != nullptr && out_dev != nullptr, "qasr_resample_pcm16: null buffer");
+  const size_t desc_bytes = align_up(sizeof(RsStream) * static_cast<size_t>(n_streams), 16);
+  const size_t total = desc_bytes + sizeof(double) * static_cast<size_t>(n_taps);
+  Staging* st = nullptr;
+  if (staging_acquire(h, total, &st) != 0) return 2;
+  RsStream* d = reinterpret_cast<RsStream*>(st->host);
+  for (int i = 0; i < n_streams; ++i)
+    d[i] = {in_offsets[i], in_offsets[i + 1] - in_offsets[i], out_offsets_out[i], out_offsets_out[i + 1] - out_offsets_out[i]};
+  std::memcpy(st->host + desc_bytes, taps, sizeof(double) * static_cast<size_t>(n_taps));
+  QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
+  QASR_LAUNCH(h, "resample_pcm16", 2.0 * static_cast<double>(in_offsets[n_streams] - in_offsets[0] + out_offsets_out[n_streams]), stream,
+              launch_resample_pcm16(pcm16_dev, reinterpret_cast<const RsStream*>(st->dev), n_streams, max_out,
+                                    reinterpret_cast<const double*>(st->dev + desc_bytes), n_taps, half_len, up, down, out_dev,
+                                    h->num_sms, stream));
+  QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
+  st->in_flight = true;
+  return 0;
+}
+
+int qasr_ws_window(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_offsets, int n_streams, const int32_t* pad_samples,
+                   const double* sos, int n_sections, int min_samples, float* out_dev, int64_t out_capacity, int64_t* out_offsets_out,
+                   void* stream_v) {
+  QASR_REQUIRE(h != nullptr && in_offsets != nullptr && out_offsets_out != nullptr && n_streams >= 0, "qasr_ws_window: bad argument");
+  QASR_REQUIRE(n_streams <= 65535, "qasr_ws_window: at most 65535 streams per call");
+  QASR_REQUIRE(min_samples >= 0, "qasr_ws_window: min_samples < 0");
+  if (sos == nullptr) n_sections = 0;
+  QASR_REQUIRE(n_sections >= 0 && n_sections <= 8, "qasr_ws_window: at most 8 second-order sections");
+  int warm = 0;
+  for (int s = 0; s < n_sections; ++s)
+    QASR_REQUIRE(sos[6 * s + 3] == 1.0, "qasr_ws_window: sos[:, 3] should be all ones (scipy.signal.sosfilt's own check)");
+  if (n_sections > 0) {
+    warm = sos_warmup(sos, n_sections);
+    QASR_REQUIRE(warm > 0, "qasr_ws_window: the filter's poles are too close to the unit circle for the blocked evaluation");
+  }
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  out_offsets_out[0] = 0;
+  long long max_out = 0;
+  for (int i = 0; i < n_streams; ++i) {
+    const int64_t n = in_offsets[i + 1] - in_offsets[i];
+    QASR_REQUIRE(n >= 0, "qasr_ws_window: offsets must be non-decreasing");
+    QASR_REQUIRE(pad_samples == nullptr || pad_samples[i] >= 0, "qasr_ws_window: negative pad");
+    const int64_t flt = n + (pad_samples != nullptr ? pad_samples[i] : 0);
+    const int64_t m = flt == 0 ? 0 : std::max<int64_t>(flt, min_samples);  // an empty window stays empty (server.py:1331-1332 returns early)
+    out_offsets_out[i + 1] = out_offsets_out[i] + m;
+    max_out = std::max<long long>(max_out, m);
+  }
+  QASR_REQUIRE(out_offsets_out[n_streams] <= out_capacity, "qasr_ws_window: out_capacity too small");
+  if (n_streams == 0 || max_out == 0) return 0;
+  QASR_REQUIRE(pcm16_dev != nullptr && out_dev != nullptr, "qasr_ws_window: null buffer");
+  const size_t total = sizeof(WsStream) * static_cast<size_t>(n_streams);
+  Staging* st = nullptr;
+  if (staging_acquire(h, total, &st) != 0) return 2;
+  WsStream* d = reinterpret_cast<WsStream*>(st->host);
+  for (int i = 0; i < n_streams; ++i) {
+    const int64_t n = in_offsets[i + 1] - in_offsets[i];
+    d[i] = {in_offsets[i], n, n + (pad_samples != nullptr ? pad_samples[i] : 0), out_offsets_out[i], out_offsets_out[i + 1] - out_offsets_out[i]};
+  }
+  QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
+  QASR_LAUNCH(h, "ws_window", 2.0 * static_cast<double>(in_offsets[n_streams] - in_offsets[0]) + 4.0 * static_cast<double>(out_offsets_out[n_streams]),
+              stream, launch_ws_window(pcm16_dev, reinterpret_cast<const WsStream*>(st->dev), n_streams, max_out, sos, n_sections, warm, out_dev, stream));
+  QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
+  st->in_flight = true;
+  return 0;
+}
+
 int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
                      int64_t* feature_lens_out, void* stream_v) {
   QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_logmel_host: bad argument");

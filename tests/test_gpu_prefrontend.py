@@ -1,0 +1,147 @@
+"""WS pre-frontend on the GPU (through the C ABI) vs the scipy-pinned oracle: int16 -> [resample] -> /32768 -> band-pass."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pre():
+    from oracle import CONFIGS, make_weights
+    from qwen3_asr_b200 import B200AudioEncoder, B200PreFrontend
+
+    cfg = CONFIGS["tiny"]
+    enc = B200AudioEncoder(cfg, make_weights(cfg, seed=1), max_chunks=64)
+    yield B200PreFrontend(enc)
+    enc.close()
+
+
+def _pcm16(n, seed, scale=6000.0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    x = scale * (0.4 * rng.standard_normal(n) + np.sin(2 * np.pi * 440 * t) + 0.5 * np.sin(2 * np.pi * 50 * t) + 0.3)
+    return np.clip(x, -32768, 32767).astype(np.int16)
+
+
+def _ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
+    bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
+    return np.abs(ai - bi)
+
+
+def test_bandpass_batch_matches_scipy_bitwise(pre):
+    import scipy.signal as ss
+
+    # ragged batch incl. lengths below / at / above the 512-sample thread block and the warm-up span, and an empty stream
+    lens = [1, 511, 512, 513, 1568, 5000, 0, 96000, 33333]
+    wins = [_pcm16(n, 100 + i) for i, n in enumerate(lens)]
+    pre.min_samples = 0
+    out, offs = pre.prepare(wins, 16000, pad_silence=None, bandpass=True)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    sos = ss.butter(4, [300, 3400], btype="bandpass", fs=16000, output="sos")
+    assert offs.tolist() == np.concatenate([[0], np.cumsum(lens)]).tolist()
+    n_diff = 0
+    for i, w in enumerate(wins):
+        want = ss.sosfilt(sos, w.astype(np.float32) / 32768.0).astype(np.float32)   # the reference's own two lines
+        got = out[offs[i]:offs[i + 1]]
+        d = _ulp_diff(got, want)
+        assert d.max(initial=0) <= 1, (i, int(d.max()))       # float64 cascade: only a rounding tie could move a float32 by one ulp
+        n_diff += int((d > 0).sum())
+    assert n_diff <= 2, n_diff
+    pre.min_samples = 8000
+
+
+def test_ws_windows_c3_shape_vs_oracle(pre):
+    from oracle import prefrontend as opf
+
+    # BASELINE config 3 shape: ragged windows, every 4th one flushing (+600 ms of silence), short ones padded to 0.5 s
+    lens = [min(96000, 7200 * (1 + (5 * i) % 14)) for i in range(16)] + [3000]
+    wins = [_pcm16(n, 200 + i) for i, n in enumerate(lens)]
+    flush = [i % 4 == 3 for i in range(len(wins))]
+    out, offs = pre.prepare(wins, 16000, pad_silence=flush, bandpass=True)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for i, w in enumerate(wins):
+        want = opf.ws_window(w, 16000, pad_silence=flush[i])
+        got = out[offs[i]:offs[i + 1]]
+        assert got.shape == want.shape, i
+        assert _ulp_diff(got, want).max() <= 1, i
+    assert offs[-1] - offs[-2] == 8000 and not out[offs[-2] + 3000:offs[-1]].any()
+
+
+@pytest.mark.parametrize("orig_sr", [8000, 44100, 48000, 22050])
+def test_resample_matches_oracle_bitwise(pre, orig_sr):
+    from oracle import prefrontend as opf
+
+    wins = [_pcm16(n, 300 + i) for i, n in enumerate([4000, 1, 777, 12345])]
+    dev, offs = pre._pack_int16(wins)
+    out, ooffs = pre.resample_pcm16_packed(dev, offs, orig_sr)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    up, down = opf.resample_ratio(orig_sr)
+    taps, _ = opf.resample_taps(up, down)
+    for i, w in enumerate(wins):
+        want = opf.resample_pcm16(w, orig_sr)
+        got = out[ooffs[i]:ooffs[i + 1]]
+        assert got.shape == want.shape
+        # built-in taps come from the C library's libm, the oracle's from numpy: allow the int16 truncation to flip on < 0.1 % of samples
+        assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1
+        assert (got != want).mean() <= 1e-3
+    # with the oracle's own taps handed over the ABI the float64 sums are the same operations in the same order: bit-exact
+    out2, ooffs2 = pre.resample_pcm16_packed(dev, offs, orig_sr, taps=taps)
+    torch.cuda.synchronize()
+    out2 = out2.cpu().numpy()
+    for i, w in enumerate(wins):
+        assert np.array_equal(out2[ooffs2[i]:ooffs2[i + 1]], opf.resample_pcm16(w, orig_sr)), i
+
+
+def test_reference_named_helpers(pre):
+    from oracle import prefrontend as opf
+
+    x = _pcm16(2400, 4)
+    assert pre.resample_pcm_bytes(x.tobytes(), 16000) == x.tobytes()            # unchanged, as in the reference
+    y = np.frombuffer(pre.resample_pcm_bytes(x.tobytes(), 8000), dtype=np.int16)
+    assert y.shape[0] == 4800 and np.abs(y.astype(np.int32) - opf.resample_pcm16(x, 8000)).max() <= 1
+    f = pre.telephony_bandpass(x)
+    assert f.dtype == np.float32 and _ulp_diff(f, opf.telephony_bandpass(x.astype(np.float32) / 32768.0)).max() <= 1
+
+
+def test_pcm_bytes_to_tokens_stays_on_gpu_and_matches_two_step_path(pre):
+    from oracle import prefrontend as opf
+
+    wins = [_pcm16(n, 400 + i) for i, n in enumerate([16000, 48000, 7000])]
+    flush = [False, True, False]
+    hid, toks = pre.encode_windows([w.tobytes() for w in wins], 16000, pad_silence=flush)
+    clips = [opf.ws_window(w, 16000, pad_silence=f) for w, f in zip(wins, flush)]
+    hid2, toks2 = pre.enc.encode_pcm(clips)
+    torch.cuda.synchronize()
+    assert toks.tolist() == toks2.tolist()
+    # identical PCM (<= 1 ulp on a vanishing fraction of samples) -> identical bf16 tokens except where a rounding boundary is hit
+    a, b = hid.float().cpu().numpy(), hid2.float().cpu().numpy()
+    assert np.abs(a - b).max() <= 2e-2 * max(1.0, np.abs(b).max())
+    assert (a != b).mean() < 0.02
+
+
+def test_rejects_bad_arguments(pre):
+    from qwen3_asr_b200 import QasrError
+
+    with pytest.raises(QasrError):
+        pre._pack_int16([np.zeros(10, np.float32)])
+    dev, offs = pre._pack_int16([_pcm16(100, 1)])
+    import ctypes as C
+    from qwen3_asr_b200 import _lib
+    out = torch.empty(100, dtype=torch.float32, device=dev.device)
+    ooffs = np.zeros(2, dtype=np.int64)
+    bad_sos = np.array([[1.0, 0, 0, 2.0, 0, 0]])      # a0 != 1: scipy.signal.sosfilt raises, so do we
+    rc = pre.lib.qasr_ws_window(pre.enc._h, C.c_void_p(dev.data_ptr()), offs.ctypes.data_as(_lib._I64P), 1, None,
+                                bad_sos.ctypes.data_as(C.POINTER(C.c_double)), 1, 0, C.c_void_p(out.data_ptr()), 100,
+                                ooffs.ctypes.data_as(_lib._I64P), None)
+    assert rc != 0 and b"all ones" in pre.lib.qasr_last_error()
+    rc = pre.lib.qasr_ws_window(pre.enc._h, C.c_void_p(dev.data_ptr()), offs.ctypes.data_as(_lib._I64P), 1, None, None, 0, 0,
+                                C.c_void_p(out.data_ptr()), 50, ooffs.ctypes.data_as(_lib._I64P), None)
+    assert rc != 0 and b"out_capacity" in pre.lib.qasr_last_error()

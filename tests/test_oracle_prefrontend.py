@@ -1,0 +1,59 @@
+"""Pins oracle/prefrontend.py (the CPU restatement of the reference's WS pre-frontend, src/server.py:26-42, 1321-1338)
+against the library functions the reference itself calls (scipy) -- CPU only."""
+
+import numpy as np
+import pytest
+import scipy.signal as ss
+
+from oracle import prefrontend as pf
+
+
+def _pcm16(n, seed, scale=6000.0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    x = scale * (0.4 * rng.standard_normal(n) + np.sin(2 * np.pi * 440 * t) + 0.5 * np.sin(2 * np.pi * 50 * t) + 0.3)
+    return np.clip(x, -32768, 32767).astype(np.int16)
+
+
+@pytest.mark.parametrize("n", [1, 7, 480, 9600, 40001])
+def test_bandpass_restatement_is_bit_exact_vs_scipy_sosfilt(n):
+    # the reference's call, verbatim (src/server.py:28-29)
+    audio = _pcm16(n, n).astype(np.float32) / 32768.0
+    sos = ss.butter(4, [300, 3400], btype="bandpass", fs=16000, output="sos")
+    want = ss.sosfilt(sos, audio).astype(np.float32)
+    got = pf.telephony_bandpass(audio)
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("up,down", [(2, 1), (1, 2), (160, 441), (3, 2), (1, 3), (320, 441)])
+def test_resample_restatement_vs_scipy_resample_poly(up, down):
+    x = _pcm16(6000, up * 1000 + down).astype(np.float64)
+    want = ss.resample_poly(x, up, down)
+    got = pf.resample_poly_f64(x, up, down)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    taps, half_len = pf.resample_taps(up, down)
+    ref = ss.firwin(2 * half_len + 1, 1.0 / max(up, down), window=("kaiser", 5.0)) * up
+    assert np.abs(taps - ref).max() <= 2e-15 * np.abs(ref).max()   # a few ulp: I0 series vs scipy.special.i0
+
+
+def test_resample_pcm16_truncates_toward_zero_like_numpy_astype():
+    x = _pcm16(4000, 5)
+    y = pf.resample_pcm16(x, 8000)
+    want = ss.resample_poly(x.astype(np.float64), 2, 1)
+    assert y.dtype == np.int16 and y.shape[0] == 8000
+    # identical except where the float64 sums straddle an integer by rounding noise (none expected on this input)
+    assert np.array_equal(y, np.trunc(want).astype(np.int16))
+    assert np.array_equal(pf.resample_pcm16(x, 16000), x)
+
+
+def test_ws_window_layout():
+    x = _pcm16(3000, 9)
+    w = pf.ws_window(x, 16000, pad_silence=True)
+    assert w.dtype == np.float32 and w.shape[0] == 3000 + 9600
+    short = pf.ws_window(x[:1000], 16000, pad_silence=False)
+    assert short.shape[0] == pf.MIN_SAMPLES and not short[1000:].any()
+    # the flush silence IS filtered (the reference appends the zeros before the band-pass): the ringing is not zero
+    assert np.abs(w[3000:3100]).max() > 0
+    raw = pf.ws_window(x, 16000, bandpass=False, min_samples=0)
+    assert np.array_equal(raw, x.astype(np.float32) / 32768.0)
