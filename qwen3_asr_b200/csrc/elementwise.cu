@@ -73,9 +73,9 @@ template <typename MelT>
 __global__ void __launch_bounds__(C1_THREADS, 2) conv1_kernel(const MelT* __restrict__ mel, long long ld, const ChunkDesc* __restrict__ chunks,
                                                               const float* __restrict__ w, const float* __restrict__ bias, int channels,
                                                               __nv_bfloat16* __restrict__ act1) {
-  // every mel value twice, {x, x}: one LDS.64 / LDS.128 hands FFMA2 its broadcast operand without a register move
-  extern __shared__ __align__(16) uint8_t c1_smem[];
-  float2 (*tile)[C1_TILE_W] = reinterpret_cast<float2 (*)[C1_TILE_W]>(c1_smem);
+  // FFMA2 takes a 32-bit register as a broadcast operand ({x, x} costs no move), so the tile holds plain floats: 15 bytes of
+  // shared-memory traffic per output (a {x, x} tile doubled that and made the kernel LDS-bandwidth bound)
+  __shared__ __align__(16) float tile[C1_TILE_H][C1_TILE_W];
   const int chunk = blockIdx.x;
   const int slot0 = blockIdx.y * C1_COLS;  // first column slot (0..51) of this CTA
   const ChunkDesc cd = chunks[chunk];
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_kernel(const MelT* __rest
     const int bin = r - 1, f = f0 + cc;
     float v = 0.f;
     if (bin >= 0 && bin < 128 && f >= 0 && f < cd.valid) v = mel_load<MelT>(mel + bin * ld + cd.mel_col0 + f);
-    tile[r][cc] = make_float2(v, v);
+    tile[r][cc] = v;
   }
   __syncthreads();
 
@@ -115,12 +115,12 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_kernel(const MelT* __rest
       f32x2_t acc = bv;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const float2* row = &tile[2 * h + kh][cc];
-        const ulonglong2 x01 = *reinterpret_cast<const ulonglong2*>(row);
-        const f32x2_t x2 = *reinterpret_cast<const f32x2_t*>(row + 2);
-        acc = fma2(wv[kh * 3 + 0], x01.x, acc);
-        acc = fma2(wv[kh * 3 + 1], x01.y, acc);
-        acc = fma2(wv[kh * 3 + 2], x2, acc);
+        const float* row = &tile[2 * h + kh][cc];
+        const float2 x01 = *reinterpret_cast<const float2*>(row);
+        const float x2 = row[2];
+        acc = fma2(wv[kh * 3 + 0], pk(x01.x, x01.x), acc);
+        acc = fma2(wv[kh * 3 + 1], pk(x01.y, x01.y), acc);
+        acc = fma2(wv[kh * 3 + 2], pk(x2, x2), acc);
       }
       const float2 a = upk(acc);
       const float2 xr = bf16_round2(a.x, a.y);
@@ -408,10 +408,7 @@ cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, con
   if (n_chunks == 0) return cudaSuccess;
   if (channels > 480 || (channels & 1)) return cudaErrorInvalidValue;
   dim3 grid(n_chunks, ACT1_PITCH / C1_COLS);
-  constexpr int smem = C1_TILE_H * C1_TILE_W * sizeof(float2);
-  cudaError_t e = mel_is_bf16 ? cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                              : cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
+  constexpr int smem = 0;
   if (mel_is_bf16)
     conv1_kernel<__nv_bfloat16><<<grid, C1_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, channels, act1);
   else
