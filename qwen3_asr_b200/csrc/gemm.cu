@@ -94,16 +94,47 @@ namespace {
 template <int BN, int AMODE, int KIND, class Epi>
 cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc::GemmShape& shape, const Epi& epi, int num_sms,
                       cudaStream_t stream) {
-  constexpr int ST = tc::default_stages<BN>();
-  using L = tc::SmemLayout<BN, ST, Epi::kScaled>;
-  auto kern = tc::gemm_tc_kernel<BN, ST, AMODE, KIND, Epi>;
+  constexpr bool CTA2 = kGemmCta2;
+  constexpr int ST = tc::default_stages<BN, CTA2>();
+  using L = tc::SmemLayout<BN, ST, Epi::kScaled, CTA2>;
+  auto kern = tc::gemm_tc_kernel<BN, ST, AMODE, KIND, CTA2, Epi>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
   if (e != cudaSuccess) return e;
-  const int tiles = shape.m_tiles * shape.n_tiles;
-  if (tiles <= 0) return cudaSuccess;
-  const int grid = std::min(tiles, num_sms);
-  kern<<<grid, tc::kThreads, L::TOTAL, stream>>>(tm_a, tm_b, shape, epi);
-  return cudaGetLastError();
+  if (shape.m_tiles <= 0 || shape.n_tiles <= 0) return cudaSuccess;
+  if constexpr (!CTA2) {
+    const int grid = std::min(shape.m_tiles * shape.n_tiles, num_sms);
+    kern<<<grid, tc::kThreads, L::TOTAL, stream>>>(tm_a, tm_b, shape, epi);
+    return cudaGetLastError();
+  } else {
+    // persistent CTA pairs: as many 2-CTA clusters as the device can keep resident at once (one CTA per SM; a GPC with an
+    // odd number of free SMs leaves one idle), never more than there are 256-row tiles
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    static thread_local int max_clusters_cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int max_clusters = dev < 64 ? max_clusters_cached[dev] : 0;
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3(2 * (num_sms / 2));
+      e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+      if (e != cudaSuccess) return e;
+      if (max_clusters <= 0) return cudaErrorLaunchOutOfResources;
+      max_clusters = std::min(max_clusters, num_sms / 2);
+      if (dev < 64) max_clusters_cached[dev] = max_clusters;
+    }
+    const int tiles = ((shape.m_tiles + 1) / 2) * shape.n_tiles;
+    cfg.gridDim = dim3(2 * std::min(tiles, max_clusters));
+    return cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, shape, epi);
+  }
 }
 
 template <class ALoad, class Epi>

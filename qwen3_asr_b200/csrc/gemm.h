@@ -23,6 +23,15 @@ int make_tmap_conv(CUtensorMap* tm, const void* base, long long g_in, int h_in, 
 // Largest supported N tile (256 / 128 / 64) that divides n; 0 if none.
 int pick_bn(int n);
 
+// The GEMM family runs as CTA pairs (tcgen05.mma.cta_group::2, see tc_gemm.cuh) unless the library is built with
+// -DQASR_GEMM_1CTA=1 (A/B builds).  In pair mode each CTA stages half of the weight tile, so the weight tensor maps
+// carry a box of bn / 2 rows.
+#ifndef QASR_GEMM_1CTA
+#define QASR_GEMM_1CTA 0
+#endif
+constexpr bool kGemmCta2 = QASR_GEMM_1CTA == 0;
+constexpr int gemm_b_box_rows(int bn) { return kGemmCta2 ? bn / 2 : bn; }
+
 enum LinearEpi : int { LIN_PLAIN = 0, LIN_GELU = 1, LIN_RESIDUAL = 2, LIN_QKV = 3 /* head-major output, see EpiQkv */ };
 
 struct LinearArgs {

@@ -295,10 +295,10 @@ int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, 
     if (dev_alloc(h, reinterpret_cast<void**>(&out->w8), nk) != 0) return 2;
     QASR_CUDA_CHECK(cudaMemcpy(out->w8, q.data(), nk, cudaMemcpyHostToDevice));
     if (upload_f32(h, sc.data(), n, &out->wscale) != 0) return 2;
-    return make_tmap_rowmajor_u8(&out->tm, out->w8, n, k, k, out->bn);
+    return make_tmap_rowmajor_u8(&out->tm, out->w8, n, k, k, gemm_b_box_rows(out->bn));
   }
   if (upload_bf16(h, w, static_cast<size_t>(n) * k, &out->w) != 0) return 2;
-  return make_tmap_rowmajor(&out->tm, out->w, n, k, k, out->bn);
+  return make_tmap_rowmajor(&out->tm, out->w, n, k, k, gemm_b_box_rows(out->bn));
 }
 
 int load_linear(qasr_handle_s* h, const std::string& prefix, int n, int k, bool bias, LinearW* out) {
@@ -325,7 +325,7 @@ int load_conv(qasr_handle_s* h, const std::string& prefix, bf16** w_out, float**
       for (int t = 0; t < 9; ++t) packed[static_cast<size_t>(o) * kConvKPad + t * 512 + i] = w->data[(static_cast<size_t>(o) * kConvC + i) * 9 + t];
   if (upload_bf16(h, packed.data(), packed.size(), w_out) != 0) return 2;
   if (upload_f32(h, b->data.data(), kConvC, b_out) != 0) return 2;
-  return make_tmap_rowmajor(tm, *w_out, kConvC, kConvKPad, kConvKPad, 240);
+  return make_tmap_rowmajor(tm, *w_out, kConvC, kConvKPad, kConvKPad, gemm_b_box_rows(240));
 }
 
 struct Unit {  // one attention window worth of chunks of one clip
@@ -1212,7 +1212,7 @@ int qasr_debug_gemm(const void* a, const void* b, const float* bias, const void*
   if (impl == 0) {
     int rc;
     if ((rc = make_tmap_rowmajor(&tm_a, a, m, k, k, 128)) != 0) return rc;
-    if ((rc = make_tmap_rowmajor(&tm_b, b, n, k, k, bn)) != 0) return rc;
+    if ((rc = make_tmap_rowmajor(&tm_b, b, n, k, k, gemm_b_box_rows(bn))) != 0) return rc;
   }
   int dev = 0, sms = kNumSMs;
   QASR_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1258,7 +1258,7 @@ int qasr_debug_gemm_fp8(const void* a8, const void* b8, const float* row_scale, 
   CUtensorMap tm_a, tm_b;
   int rc;
   if ((rc = make_tmap_rowmajor_u8(&tm_a, a8, m, k, k, 128)) != 0) return rc;
-  if ((rc = make_tmap_rowmajor_u8(&tm_b, b8, n, k, k, bn)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor_u8(&tm_b, b8, n, k, k, gemm_b_box_rows(bn))) != 0) return rc;
   int dev = 0, sms = kNumSMs;
   QASR_CUDA_CHECK(cudaGetDevice(&dev));
   QASR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -17,6 +17,13 @@
 //                                     segments to global (+ residual / positional addend, prefetched)
 // Pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) mbarriers, so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// CTA2 = true (the product configuration): the two CTAs of a 2-CTA cluster (one TPC) work on one 256 x BN tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and only HALF of the B tile (BN / 2 weight rows); the
+// tensor cores of both SMs read the two halves, so the shared-memory bytes written and read per FLOP drop by a third
+// and a stage is 32 KB instead of 48 KB (6-deep ring).  Only the leader CTA (cluster rank 0) issues MMAs; every TMA of
+// the pair signals the leader's full barrier, tcgen05.commit multicasts "stage free" / "accumulator ready" to both
+// CTAs, and both CTAs' epilogue warps release the accumulator on the leader's TMEM-empty barrier.
 #pragma once
 
 #include <cuda.h>
@@ -116,6 +123,39 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// ---- 2-CTA (cta_group::2) variants ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA (the pair's leader)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster_addr)
+      : "memory");
+}
+
 // One lane of a converged warp (elect.sync): ptxas then knows the guarded region runs on exactly one lane and issues
 // the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of serialising over "active lanes".
 __device__ __forceinline__ bool elect_one() {
@@ -134,6 +174,13 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -156,6 +203,31 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t 
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// cta_group::2: M = 256 over the CTA pair; issued by ONE thread of the leader CTA.
+template <int KIND>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND == K_E4M3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive on the barrier at this smem offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
@@ -193,9 +265,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 
 // SCALED (fp8 kinds): bias and column-scale tables are single-buffered (an extra epilogue barrier per tile keeps a fast
 // warp from overwriting them) -- with 4 stages of 48 KB and 32 KB of staging there is no room for two copies of both.
-template <int BN, int STAGES, bool SCALED = false>
+template <int BN, int STAGES, bool SCALED = false, bool CTA2 = false>
 struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;   // weight rows staged by this CTA (the pair's other CTA stages the rest)
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;               // [kEpiWarps][32 rows][128 B]
   static constexpr int TAB_BUFS = SCALED ? 1 : 2;
@@ -208,8 +281,8 @@ struct SmemLayout {
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
-template <int BN>
-constexpr int default_stages() { return BN > 192 ? 4 : (BN > 128 ? 4 : 6); }
+template <int BN, bool CTA2 = false>
+constexpr int default_stages() { return CTA2 ? 6 : (BN > 192 ? 4 : (BN > 128 ? 4 : 6)); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
@@ -229,10 +302,11 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 //   offset(m, n)          element offset of 8 consecutive output columns, or -1 to skip them
 //   prefetch / finish     optional post-rounding addend (residual, positional table) and the final store
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int AMODE, int KIND, class Epi>
+template <int BN, int STAGES, int AMODE, int KIND, bool CTA2, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape, Epi epi) {
-  using L = SmemLayout<BN, STAGES, Epi::kScaled>;
+  using L = SmemLayout<BN, STAGES, Epi::kScaled, CTA2>;
+  static_assert(!CTA2 || BN % 16 == 0, "UMMA N for M=256 must be a multiple of 16; each CTA stages BN / 2 rows (whole 8-row swizzle atoms)");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(BN <= kAccStride, "an accumulator stage is kAccStride TMEM columns");
   static_assert(KIND == K_BF16 || AMODE == A_LINEAR, "the implicit-GEMM convolutions stay bf16 (torchao quantises nn.Linear only)");
@@ -252,7 +326,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = shape.m_tiles * shape.n_tiles;
+  // CTA2: a "tile" is 256 rows (two m blocks, one per CTA of the pair) and the pair walks the tile list together
+  const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int num_tiles = (CTA2 ? (shape.m_tiles + 1) / 2 : shape.m_tiles) * shape.n_tiles;
+  const int tile0 = CTA2 ? blockIdx.x >> 1 : blockIdx.x;
+  const int tile_step = CTA2 ? gridDim.x >> 1 : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -265,13 +343,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarps);  // one elected lane of each epilogue warp
+      mbar_init(&tmem_empty_bar[i], (CTA2 ? 2 : 1) * kEpiWarps);  // one elected lane of each epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  if (warp == 2) {
+    if constexpr (CTA2) tmem_alloc_pair(tmem_ptr_smem, kTmemCols);
+    else tmem_alloc(tmem_ptr_smem, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -279,8 +361,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / shape.n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = CTA2 ? 2 * (tile / shape.n_tiles) + rank : tile / shape.n_tiles;
       const int n_blk = tile % shape.n_tiles;
       int tap = 0, cb = 0;
       for (int kb = 0; kb < shape.num_kb; ++kb) {
@@ -288,33 +370,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          if constexpr (AMODE == A_LINEAR) {
-            tma_load_2d(sa, &tmA, kb * KB_ELEMS, m_blk * BLOCK_M, &full_bar[stage]);
+          if constexpr (CTA2) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (a row block past the end of A is zero-filled
+            // by the TMA unit and still counts its full box)
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+            if constexpr (AMODE == A_LINEAR) {
+              tma_load_2d_pair(sa, &tmA, kb * KB_ELEMS, m_blk * BLOCK_M, bar);
+            } else {
+              const int kh = tap / 3, kw = tap - kh * 3;
+              tma_load_3d_pair(sa, &tmA, cb * KB_ELEMS, kh - 1, 2 * (m_blk * shape.gt) + kw, bar);
+            }
+            tma_load_2d_pair(sb, &tmB, kb * KB_ELEMS, n_blk * BN + rank * L::B_ROWS, bar);
           } else {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            // input column = 2 * (global output column) + kw (left zero column is part of the layout),
-            // input row    = 2 * (output row) + kh - 1    (row -1 is out of bounds -> TMA zero fill)
-            tma_load_3d(sa, &tmA, cb * KB_ELEMS, kh - 1, 2 * (m_blk * shape.gt) + kw, &full_bar[stage]);
+            mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            if constexpr (AMODE == A_LINEAR) {
+              tma_load_2d(sa, &tmA, kb * KB_ELEMS, m_blk * BLOCK_M, &full_bar[stage]);
+            } else {
+              const int kh = tap / 3, kw = tap - kh * 3;
+              // input column = 2 * (global output column) + kw (left zero column is part of the layout),
+              // input row    = 2 * (output row) + kh - 1    (row -1 is out of bounds -> TMA zero fill)
+              tma_load_3d(sa, &tmA, cb * KB_ELEMS, kh - 1, 2 * (m_blk * shape.gt) + kw, &full_bar[stage]);
+            }
+            tma_load_2d(sb, &tmB, kb * KB_ELEMS, n_blk * BN, &full_bar[stage]);
           }
-          tma_load_2d(sb, &tmB, kb * KB_ELEMS, n_blk * BN, &full_bar[stage]);
         }
         __syncwarp();
         if (++cb == shape.kb_per_tap) { cb = 0; ++tap; }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (CTA2: the leader CTA only) =====================
     // The whole warp walks the pipeline (converged waits); one elected lane issues.  Descriptor bases of the ring's
     // stages are loop invariants; the per-k advance (one UMMA = 32 bytes of K inside the 128B swizzle atom: 16 bf16 or
     // 32 e4m3) is +2 in the >>4 address field.
-    constexpr uint32_t idesc = KIND == K_E4M3 ? make_idesc_e4m3(BLOCK_M, BN) : make_idesc_bf16(BLOCK_M, BN);
+    constexpr int UM = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+    constexpr uint32_t idesc = KIND == K_E4M3 ? make_idesc_e4m3(UM, BN) : make_idesc_bf16(UM, BN);
     const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem));
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       wait_tmem_empty(&tmem_empty_bar[as], aphase ^ 1);
@@ -326,11 +423,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t da = desc0 + static_cast<uint64_t>((stage * L::STAGE_BYTES) >> 4);
         const uint64_t db = da + static_cast<uint64_t>(A_STAGE_BYTES >> 4);
         if (elect_one()) {
+          if constexpr (CTA2) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K_BYTES / 32; ++k)
-            umma<KIND>(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (kb == shape.num_kb - 1) umma_commit(&tmem_full_bar[as]);
+            for (int k = 0; k < BLOCK_K_BYTES / 32; ++k)
+              umma_pair<KIND>(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == shape.num_kb - 1) umma_commit_pair(&tmem_full_bar[as]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K_BYTES / 32; ++k)
+              umma<KIND>(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (kb == shape.num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -348,8 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NP = (BN + kPanel - 1) / kPanel;
     const int sub = lane >> 3, ch = lane & 7;  // phase B: row within a 4-row group, 16-byte chunk of the row segment
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-      const int m_blk = tile / shape.n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
+      const int m_blk = CTA2 ? 2 * (tile / shape.n_tiles) + rank : tile / shape.n_tiles;
       const int n_blk = tile % shape.n_tiles;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
@@ -441,16 +546,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tmem_empty_bar[as]);
+      }
       if constexpr (L::TAB_BUFS == 1) named_bar_sync(2, kEpiThreads);  // everyone is done with the single-buffered tables
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // neither CTA may free TMEM or exit while the pair's MMAs / remote arrivals are in flight
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CTA2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
