@@ -8,12 +8,13 @@
 //   * conv_out (K5): A is conv3's output viewed as [chunk*13, 16*480].
 // B is always an nn.Linear-style [N,K] row-major (K-major) weight.
 //
-// Roles (256 threads, 1 CTA per SM, grid = #SMs):
+// Roles (640 threads, 1 CTA per SM, grid = #SMs):
 //   warp 0 lane 0 : TMA producer   -- cp.async.bulk.tensor into a kStages-deep 128B-swizzled ring
 //   warp 1 lane 0 : MMA issuer     -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage
 //   warp 2        : TMEM allocator -- 512 columns = two accumulator stages
-//   warps 4..11   : epilogue       -- two warps per TMEM lane quarter, 64-column panels: tcgen05.ld -> bias (from
-//                                     smem) / activation -> bf16 -> swizzled smem staging -> coalesced 128-byte row
+//   warps 4..19   : epilogue       -- four warps per TMEM lane quarter (a GELU epilogue on 8 warps took longer than the
+//                                     K = 1024 main loop of its tile), 32-column panels: tcgen05.ld -> bias (from
+//                                     smem) / activation -> bf16 -> swizzled smem staging -> coalesced 64-byte row
 //                                     segments to global (+ residual / positional addend, prefetched)
 // Pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) mbarriers, so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
@@ -41,10 +42,10 @@ enum Kind : int { K_BF16 = 0, K_E4M3 = 1 };  // kind::f16 (bf16 x bf16) / kind::
 template <int KIND>
 constexpr int block_k_elems() { return KIND == K_E4M3 ? 128 : 64; }
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 384
-constexpr int kPanel = 64;            // epilogue panel: 64 bf16 columns = one 128-byte row segment
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 640
+constexpr int kPanel = 32;            // epilogue panel: 32 bf16 columns = one 64-byte row segment
 constexpr int kStagingBytes = 32 * kPanel * 2;  // per epilogue warp
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage (2 stages)
@@ -139,8 +140,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of a peer CTA.  Default semantics (as CUTLASS's ClusterBarrier::arrive): a .release.cluster
+// arrive made every epilogue warp drain its global stores first (26 % of the GELU epilogue's stall samples); the only
+// ordering this arrive has to carry -- TMEM reads before the next tile's MMAs -- comes from tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA (the pair's leader)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster_addr) {
@@ -445,13 +449,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue =====================
     const int ew = warp - kEpiWarp0;
     const int q = ew & 3;       // == warp % 4: the TMEM lane quarter this warp may read
-    const int half = ew >> 2;   // the two warps of a quarter take alternate 64-column panels
+    const int pw = ew >> 2;     // the four warps of a quarter take every fourth 32-column panel
     const int et = threadIdx.x - kEpiWarp0 * 32;
     const uint32_t stage_base = smem_u32(smem + L::STAGING_OFFSET + ew * kStagingBytes);
     float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
     float* scale_s = reinterpret_cast<float*>(smem + L::SCALE_OFFSET);
     constexpr int NP = (BN + kPanel - 1) / kPanel;
-    const int sub = lane >> 3, ch = lane & 7;  // phase B: row within a 4-row group, 16-byte chunk of the row segment
+    const int sub = lane >> 2, ch = lane & 3;  // phase B: row within an 8-row group, 16-byte chunk of the 64-byte row segment
     int iter = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
       const int m_blk = CTA2 ? 2 * (tile / shape.n_tiles) + rank : tile / shape.n_tiles;
@@ -480,20 +484,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (Epi::kScaled) row_scale = epi.row_scale(row0 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
 #pragma unroll 1
-      for (int p = half; p < NP; p += 2) {
+      for (int p = pw; p < NP; p += kEpiWarps / 4) {
         const int c0 = p * kPanel;
         const int ncols = BN - c0 < kPanel ? BN - c0 : kPanel;
         // destinations of phase B + prefetch of the post-rounding addend (hidden behind phase A)
-        long long offs[8];
-        typename Epi::Prefetch pre[8];
+        long long offs[4];
+        typename Epi::Prefetch pre[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = row0 + i * 4 + sub;
+        for (int i = 0; i < 4; ++i) {
+          const int m = row0 + i * 8 + sub;
           const int n = n_blk * BN + c0 + ch * 8;
           offs[i] = ch * 8 < ncols ? epi.offset(m, n) : -1;
           if (offs[i] >= 0) pre[i] = epi.prefetch(m, n, offs[i]);
         }
-        // phase A: TMEM -> registers -> bias / activation -> bf16 -> staging (row = lane, 16-byte chunks XOR-swizzled)
+        // phase A: TMEM -> registers -> bias / activation -> bf16 -> staging (row = lane, 64-byte rows whose 16-byte
+        // chunks are XOR-swizzled with (row >> 1) & 3: conflict-free for the row-per-lane writes and the phase-B reads)
         uint32_t v[kPanel];
 #pragma unroll
         for (int g = 0; g < kPanel / 16; ++g)
@@ -529,16 +534,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             pk.y = pack_bf16x2(o[2], o[3]);
             pk.z = pack_bf16x2(o[4], o[5]);
             pk.w = pack_bf16x2(o[6], o[7]);
-            st_shared_v4(stage_base + lane * 128 + ((j ^ (lane & 7)) << 4), pk);
+            st_shared_v4(stage_base + lane * (kPanel * 2) + ((j ^ ((lane >> 1) & 3)) << 4), pk);
           }
         }
         __syncwarp();
-        // phase B: each instruction moves four complete 128-byte row segments
+        // phase B: each instruction moves eight complete 64-byte row segments
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           if (offs[i] >= 0) {
-            const int r = i * 4 + sub;
-            const uint4 sv = ld_shared_v4(stage_base + r * 128 + ((ch ^ (r & 7)) << 4));
+            const int r = i * 8 + sub;
+            const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
             epi.finish(offs[i], sv, pre[i]);
           }
         }
