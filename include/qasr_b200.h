@@ -176,6 +176,28 @@ QASR_API int qasr_ws_window(qasr_handle_t h, const int16_t* pcm16_dev, const int
 
 QASR_API void qasr_destroy(qasr_handle_t h);
 
+/* ---- one process, several GPUs -----------------------------------------------------------
+ * The path shards by clip with no exchange step, so the pool is N independent handles (weights replicated), one worker
+ * thread + CUDA stream per device, and NO collective (NCCL is not used).  A batch is cut into at most N contiguous clip
+ * ranges of near-equal work; every shard reads its slice of the caller's (pinned) PCM buffer and writes its slice of the
+ * caller's output buffer directly, in clip order.  Stands where a multi-GPU deployment of the reference would run one
+ * server process per GPU behind the gateway (src/gateway.py / src/worker.py). */
+typedef struct qasr_pool_s* qasr_pool_t;
+QASR_API int qasr_pool_create(const qasr_config_t* cfg, const int* devices, int n_devices, qasr_pool_t* out);
+QASR_API int qasr_pool_size(qasr_pool_t p);
+/* qasr_set_weight / qasr_finalize / qasr_workspace_bytes for every handle of the pool */
+QASR_API int qasr_pool_set_weight(qasr_pool_t p, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
+QASR_API int qasr_pool_finalize(qasr_pool_t p);
+QASR_API size_t qasr_pool_workspace_bytes(qasr_pool_t p);
+/* qasr_submit_pcm_host across the pool.  Returns at once; token_lens_out [n_clips] and (optionally) clip_device_out
+ * [n_clips] (the CUDA device each clip was sent to) are filled before it returns.  pcm_host, clip_offsets' data and
+ * out_host must stay valid until qasr_pool_collect(ticket) returns; any number of batches may be in flight (each worker
+ * keeps two on its GPU).  out_host: bf16 [sum tokens, output_dim] in clip order. */
+QASR_API int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+                              int64_t out_capacity_tokens, int64_t* token_lens_out, int32_t* clip_device_out, uint64_t* ticket_out);
+QASR_API int qasr_pool_collect(qasr_pool_t p, uint64_t ticket);
+QASR_API void qasr_pool_destroy(qasr_pool_t p);
+
 /* ---- launch accounting and per-launch timing (measurement; bench.py's roofline figures) ------- */
 /* Number of CUDA kernels this handle has launched so far. */
 QASR_API uint64_t qasr_launch_count(qasr_handle_t h);

@@ -8,6 +8,7 @@ the ONNX_ENCODER_PATH / TRT_ENCODER_PATH slots).  Hand-written CUDA behind a C A
 from ._lib import QasrError, load_library  # noqa: F401
 from .encoder import B200AudioEncoder, EncoderOutput, make_config, sinusoid_table  # noqa: F401
 
+from .pool import B200EncoderPool  # noqa: F401
 from .prefrontend import B200PreFrontend  # noqa: F401
 
-__all__ = ["B200AudioEncoder", "B200PreFrontend", "EncoderOutput", "QasrError", "load_library", "make_config", "sinusoid_table"]
+__all__ = ["B200AudioEncoder", "B200EncoderPool", "B200PreFrontend", "EncoderOutput", "QasrError", "load_library", "make_config", "sinusoid_table"]

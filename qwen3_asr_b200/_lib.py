@@ -54,6 +54,14 @@ SIGNATURES = {
     "qasr_ws_window": (C.c_int, [_P, _P, _I64P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_int, _P, C.c_int64,
                                  _I64P, _P]),
     "qasr_destroy": (None, [_P]),
+    "qasr_pool_create": (C.c_int, [C.POINTER(QasrConfig), C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "qasr_pool_size": (C.c_int, [_P]),
+    "qasr_pool_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int, _I64P, C.c_int]),
+    "qasr_pool_finalize": (C.c_int, [_P]),
+    "qasr_pool_workspace_bytes": (C.c_size_t, [_P]),
+    "qasr_pool_submit": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
+    "qasr_pool_collect": (C.c_int, [_P, C.c_uint64]),
+    "qasr_pool_destroy": (None, [_P]),
     "qasr_launch_count": (C.c_uint64, [_P]),
     "qasr_profile_enable": (C.c_int, [_P, C.c_int]),
     "qasr_profile_read": (C.c_int, [_P, C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(HERE, "libqasr_b200.so")
-SOURCES = ["qasr.cu", "gemm.cu", "mel.cu", "elementwise.cu", "quant.cu", "attention_tc.cu", "prefrontend.cu"]
+SOURCES = ["qasr.cu", "gemm.cu", "mel.cu", "elementwise.cu", "quant.cu", "attention_tc.cu", "prefrontend.cu", "pool.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
