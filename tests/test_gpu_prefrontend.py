@@ -154,3 +154,29 @@ def test_rejects_bad_arguments(pre):
     rc = pre.lib.qasr_ws_window(pre.enc._h, C.c_void_p(dev.data_ptr()), offs.ctypes.data_as(_lib._I64P), 1, None, None, 0, 0,
                                 C.c_void_p(out.data_ptr()), 50, ooffs.ctypes.data_as(_lib._I64P), None)
     assert rc != 0 and b"out_capacity" in pre.lib.qasr_last_error()
+
+
+def test_window_batcher_over_the_real_encoder(pre):
+    """concurrently submitted windows are gathered into one ragged encoder call; every client gets exactly the
+    tokens a lone call would have produced (the kernels are batch-invariant)."""
+    import threading
+
+    from qwen3_asr_b200.batcher import WindowBatcher
+
+    wins = [_pcm16(n, 500 + i).tobytes() for i, n in enumerate([16000, 9000, 48000, 20000, 31234, 8000])]
+    flush = [i % 3 == 2 for i in range(len(wins))]
+    b = WindowBatcher(lambda w, f: pre.encode_windows(w, 16000, pad_silence=f), max_wait_ms=200.0)
+    futs = [None] * len(wins)
+
+    def client(i):
+        futs[i] = b.submit(wins[i], flush=flush[i])
+    ts = [threading.Thread(target=client, args=(i,)) for i in range(len(wins))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    outs = [f.result(timeout=30) for f in futs]
+    b.close()
+    assert sum(b.batches) == len(wins) and len(b.batches) <= 2
+    for i in range(len(wins)):
+        alone, _ = pre.encode_windows([wins[i]], 16000, pad_silence=[flush[i]])
+        torch.cuda.synchronize()
+        assert torch.equal(outs[i], alone), i
