@@ -11,10 +11,14 @@
 //   warp 1        MMA issuer: S = Q K^T (kind::f16, M = 128, N = keys rounded to 16, K = 64) into TMEM;
 //                 O = P V with P read from TMEM (A operand) and V used as an MN-major B operand straight from its
 //                 row-major tile -- no transposes, no smem round trip for S or P
-//   warp 2        TMEM allocation (2 slots x (128 S/P columns + 64 O columns))
-//   warps 4-7 / 8-11   two softmax warpgroups (thread = query row) alternating over items: tcgen05.ld S -> mask -> max ->
+//   warp 2        TMEM allocation: 4 slots x 128 columns.  A slot holds S (<= 128 fp32 columns); P (bf16 pairs) overwrites its
+//                 first 64 columns as the softmax proceeds, and O (64 fp32 columns) is accumulated into columns 64..127 --
+//                 the upper half of S, dead once the whole row has been read -- so four items fit where two did
+//   warps 4-19    four softmax warpgroups (thread = query row), item i served by warpgroup i % 4: tcgen05.ld S -> mask -> max ->
 //                 exp2 -> row sum -> bf16 P back into the S columns (tcgen05.st) -> after the second MMA, O / sum -> bf16 -> HBM
-// so the tensor core runs item i+1's QK^T while warpgroup A is in item i's softmax and warpgroup B finishes item i-1.
+// An item's softmax is a latency chain (TMEM round trips, 100+ dependent MUFU / FMNMX per row), so throughput comes from the
+// number of items in flight: four warpgroups, QK^T issued two items ahead of PV, and a 5-stage TMA ring (tiles of 112 rows
+// when every window fits, as with the checkpoints' 104-token windows).
 #include <algorithm>
 
 #include "kernels.h"
@@ -25,15 +29,23 @@ namespace {
 
 using namespace tc;
 
-constexpr int AT_THREADS = 12 * 32;
+constexpr int AT_SLOTS = 4;                       // TMEM slots == softmax warpgroups == items in the softmax stage at once
+constexpr int AT_THREADS = (4 + 4 * AT_SLOTS) * 32;  // 640
 constexpr int AT_HD = 64;
-constexpr int AT_ROWS = 128;                      // tokens per tile (window length <= 128)
-constexpr int AT_TILE_BYTES = AT_ROWS * AT_HD * 2;  // 16 KB
-constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;   // Q, K, V
-constexpr int AT_STAGES = 4;                      // smem ring (TMA runs up to 4 items ahead); TMEM slots alternate per item
-constexpr int AT_SLOT_COLS = 192;                 // TMEM: 128 columns S (P aliases the first 64) + 64 columns O
-constexpr int AT_SMEM = AT_STAGES * AT_STAGE_BYTES + 256;
-static_assert(AT_SMEM <= 232448, "exceeds the shared memory a CTA can opt in to");
+constexpr int AT_ROWS = 128;                      // query rows of the MMA (TMEM lanes); window length <= 128
+constexpr int AT_SLOT_COLS = 128;                 // TMEM: S in columns 0..127, P aliases 0..63, O aliases 64..127
+constexpr int AT_O_COL = 64;
+constexpr int AT_LOOKAHEAD = 2;                   // QK^T of item i + 2 is issued before PV of item i
+// TR = token rows per TMA tile: 112 when every window fits (14 KB tiles, 5 stages), else 128 (16 KB tiles, 4 stages)
+template <int TR>
+struct AtCfg {
+  static constexpr int TILE_BYTES = TR * AT_HD * 2;
+  static constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // Q, K, V
+  static constexpr int STAGES = TR <= 112 ? 5 : 4;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 256;
+  static_assert(STAGE_BYTES % 1024 == 0, "stages keep the 1024-byte alignment of SWIZZLE_128B tiles");
+  static_assert(SMEM <= 232448, "exceeds the shared memory a CTA can opt in to");
+};
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -68,18 +80,20 @@ __device__ __forceinline__ uint32_t at_idesc(int n, int b_mn) {
          (static_cast<uint32_t>(AT_ROWS >> 4) << 24);
 }
 
+template <int TR>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __restrict__ win, int n_win, int heads, int d, int head_rows,
                     __nv_bfloat16* __restrict__ out, float scale_log2e) {
+  constexpr int AT_STAGES = AtCfg<TR>::STAGES, AT_STAGE_BYTES = AtCfg<TR>::STAGE_BYTES, AT_TILE_BYTES = AtCfg<TR>::TILE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_STAGES * AT_STAGE_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES] TMA -> MMA: Q, K, V of the stage have landed
   uint64_t* empty_bar = bars + AT_STAGES;       // [STAGES] MMA -> TMA: both products of the item have read the stage
-  uint64_t* s_full = bars + 2 * AT_STAGES;      // [2] MMA -> softmax: S is in TMEM
-  uint64_t* p_full = s_full + 2;                // [2] softmax -> MMA: P is in TMEM
-  uint64_t* o_full = s_full + 4;                // [2] MMA -> softmax: O is in TMEM
-  uint64_t* o_empty = s_full + 6;               // [2] softmax -> MMA: the slot's O columns are drained
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 8);
+  uint64_t* s_full = bars + 2 * AT_STAGES;      // [SLOTS] MMA -> softmax: S is in TMEM
+  uint64_t* p_full = s_full + AT_SLOTS;         // [SLOTS] softmax -> MMA: P is in TMEM
+  uint64_t* o_full = s_full + 2 * AT_SLOTS;     // [SLOTS] MMA -> softmax: O is in TMEM
+  uint64_t* o_empty = s_full + 3 * AT_SLOTS;    // [SLOTS] softmax -> MMA: the slot is drained (O aliases S: the next QK^T waits for it)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 4 * AT_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_win * heads;
@@ -90,7 +104,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < AT_SLOTS; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);      // one elected lane per softmax warp
       mbar_init(&o_full[i], 1);
@@ -125,16 +139,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // software-pipelined: S(i+1) = Q K^T is issued before O(i) = P V, so the tensor core has work while item i is in softmax.
-    // tcgen05 operations execute in issue order: S(i+2) may overwrite the slot's S/P columns as soon as P V(i) has been
-    // issued -- only the O columns have to wait for the softmax warpgroup (o_empty).
+    // software-pipelined: S(i + AT_LOOKAHEAD) = Q K^T is issued before O(i) = P V, so several items are in softmax at once.
+    // A slot is reused by item i + AT_SLOTS; since O lives in the upper half of the S columns, that item's Q K^T waits
+    // until the softmax warpgroup has drained O(i) (o_empty).  P V(i) is issued AT_SLOTS - AT_LOOKAHEAD iterations before
+    // that wait, so the chain o_full -> drain -> o_empty is never waiting on this warp: no deadlock.
     const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem));
     auto issue_qk = [&](int it, int item) {
-      const int s = it % AT_STAGES, t = it & 1;
+      const int s = it % AT_STAGES, t = it % AT_SLOTS;
       const uint32_t ph = (it / AT_STAGES) & 1;
+      const uint32_t pht = (it / AT_SLOTS) & 1;
       const int wl = __ldg(&win[item / heads]).y;
       const int n16 = (wl + 15) >> 4;
       at_wait(&full_bar[s], ph);
+      at_wait(&o_empty[t], pht ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dq = desc0 + static_cast<uint64_t>((s * AT_STAGE_BYTES) >> 4);
@@ -148,18 +165,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       __syncwarp();
     };
     auto issue_pv = [&](int it, int item) {
-      const int s = it % AT_STAGES, t = it & 1;
-      const uint32_t pht = (it >> 1) & 1;
+      const int s = it % AT_STAGES, t = it % AT_SLOTS;
+      const uint32_t pht = (it / AT_SLOTS) & 1;
       const int wl = __ldg(&win[item / heads]).y;
       const int n16 = (wl + 15) >> 4;
       at_wait(&p_full[t], pht);
-      at_wait(&o_empty[t], pht ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dv = desc0 + static_cast<uint64_t>((s * AT_STAGE_BYTES + 2 * AT_TILE_BYTES) >> 4);
         const uint32_t idesc = at_idesc(AT_HD, 1);
         const uint32_t t_p = tmem_base + static_cast<uint32_t>(t * AT_SLOT_COLS);
-        const uint32_t t_o = t_p + 128;
+        const uint32_t t_o = t_p + AT_O_COL;
         for (int k = 0; k < n16; ++k)  // 16 keys per step: 8 packed-bf16 columns of P, 16 rows (2048 bytes) of V
           umma_bf16_ts(t_o, t_p + static_cast<uint32_t>(8 * k), dv + static_cast<uint64_t>(128 * k), idesc, k != 0 ? 1u : 0u);
         umma_commit(&o_full[t]);
@@ -167,22 +183,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       }
       __syncwarp();
     };
-    int it = 0, prev_item = -1;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    static_assert(AT_LOOKAHEAD >= 1 && AT_LOOKAHEAD < AT_SLOTS, "P V(i) must be issued before Q K^T(i + AT_SLOTS) waits for its drain");
+    const int step = gridDim.x;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += step, ++it) {
       issue_qk(it, item);
-      if (prev_item >= 0) issue_pv(it - 1, prev_item);
-      prev_item = item;
+      if (it >= AT_LOOKAHEAD) issue_pv(it - AT_LOOKAHEAD, item - AT_LOOKAHEAD * step);
     }
-    if (prev_item >= 0) issue_pv(it - 1, prev_item);
+    for (int j = it >= AT_LOOKAHEAD ? it - AT_LOOKAHEAD : 0; j < it; ++j) issue_pv(j, static_cast<int>(blockIdx.x) + j * step);
   } else if (warp >= 4) {
     // ===================== softmax + output warpgroups =====================
-    const int wg = (warp - 4) >> 2;            // 0 / 1: this warpgroup serves items whose slot == wg
+    const int wg = (warp - 4) >> 2;            // 0 .. AT_SLOTS-1: this warpgroup serves items whose slot == wg
     const int q = warp & 3;                    // TMEM lane quarter of this warp
     const int row = q * 32 + lane;             // query row == TMEM lane
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      if ((it & 1) != wg) continue;
-      const uint32_t ph = (it >> 1) & 1;
+      if (it % AT_SLOTS != wg) continue;
+      const uint32_t ph = (it / AT_SLOTS) & 1;
       const int w = item / heads, h = item - w * heads;
       const int2 wd = __ldg(&win[w]);
       const int wl = wd.y;
@@ -276,24 +293,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       tc_fence_after();
       const float inv = 1.0f / sum;
       __nv_bfloat16* orow = out + (static_cast<long long>(wd.x) + row) * d + h * AT_HD;
-      uint32_t o[AT_HD];
+      uint4 packed[AT_HD / 8];
 #pragma unroll
-      for (int g = 0; g < AT_HD / 16; ++g) tmem_ld16(t_s + 128 + g * 16, o + g * 16);
-      tmem_ld_wait();
-      if (row < wl) {
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o[32];
+        tmem_ld16(t_s + AT_O_COL + half * 32, o);
+        tmem_ld16(t_s + AT_O_COL + half * 32 + 16, o + 16);
+        tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < AT_HD / 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           uint4 a;
           a.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
           a.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
           a.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
           a.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[g] = a;
+          packed[half * 4 + g] = a;
         }
       }
+      // the slot may be overwritten by the next item's Q K^T as soon as every warp has its O row in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[wg]);
+      if (row < wl) {
+#pragma unroll
+        for (int g = 0; g < AT_HD / 8; ++g) reinterpret_cast<uint4*>(orow)[g] = packed[g];
+      }
     }
   }
 
@@ -307,16 +331,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
 
 }  // namespace
 
-// tm_qkv: make_tmap_rowmajor over the head-major qkv activation viewed as [3 * heads * head_rows, 64], box rows = 128
-cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len, int d,
-                                       int heads, int head_rows, int num_sms, cudaStream_t stream) {
+// Token rows per TMA tile for a given longest window: the tensor map's box rows must be this value.
+int attention_tc_tile_rows(int max_win_len) { return max_win_len <= 112 ? 112 : 128; }
+
+// tm_qkv: make_tmap_rowmajor over the head-major qkv activation viewed as [3 * heads * head_rows, 64], box rows =
+// attention_tc_tile_rows(longest window the handle can see)
+cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, int tile_rows, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len,
+                                       int d, int heads, int head_rows, int num_sms, cudaStream_t stream) {
   if (n_win == 0) return cudaSuccess;
-  if (d != heads * AT_HD || max_win_len > AT_ROWS) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-  if (e != cudaSuccess) return e;
+  if (d != heads * AT_HD || max_win_len > AT_ROWS || max_win_len > tile_rows || (tile_rows != 112 && tile_rows != 128)) return cudaErrorInvalidValue;
   const float scale_log2e = 0.125f * 1.44269504088896340736f;  // head_dim^-0.5 * log2(e)
   const int grid = std::min(n_win * heads, num_sms);
-  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, head_rows, out, scale_log2e);
+  cudaError_t e;
+  if (tile_rows == 112) {
+    e = cudaFuncSetAttribute(attention_tc_kernel<112>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<112>::SMEM);
+    if (e != cudaSuccess) return e;
+    attention_tc_kernel<112><<<grid, AT_THREADS, AtCfg<112>::SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, head_rows, out, scale_log2e);
+  } else {
+    e = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<128>::SMEM);
+    if (e != cudaSuccess) return e;
+    attention_tc_kernel<128><<<grid, AT_THREADS, AtCfg<128>::SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, head_rows, out, scale_log2e);
+  }
   return cudaGetLastError();
 }
 

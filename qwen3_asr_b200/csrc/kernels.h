@@ -76,8 +76,9 @@ cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out
                                     int max_win_len, int d, int heads, int head_rows, cudaStream_t stream);
 
 // tcgen05 version (attention_tc.cu): windows up to 128 tokens; tm_qkv = 128B-swizzled map over the same buffer viewed as
-// [3 * heads * head_rows, 64], box 64 x 128
-cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, __nv_bfloat16* out, const int2* win, int n_win, int max_win_len,
-                                       int d, int heads, int head_rows, int num_sms, cudaStream_t stream);
+// [3 * heads * head_rows, 64], box 64 x attention_tc_tile_rows(longest window) -- pass the same value as tile_rows
+int attention_tc_tile_rows(int max_win_len);
+cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, int tile_rows, __nv_bfloat16* out, const int2* win, int n_win,
+                                       int max_win_len, int d, int heads, int head_rows, int num_sms, cudaStream_t stream);
 
 }  // namespace qasr

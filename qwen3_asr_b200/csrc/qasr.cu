@@ -102,6 +102,7 @@ struct qasr_handle_s {
   bool simt = false;        // QASR_DEBUG_SIMT=1: run every GEMM through the SIMT checker kernel
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
   int chunks_per_window = 8;
+  int attn_tile_rows = 128;  // token rows of the attention kernel's TMA tiles (112 when every window fits)
   int max_chunks = 0, max_tokens = 0;
   int head_rows = 0;        // token capacity of one (section, head) plane of the head-major qkv buffer
 
@@ -454,7 +455,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     if ((rc = linear("qkv_gemm", tk * 3 * d * d, &h->tm_h, ln_out, L.qkv, LIN_QKV, h->qkv, 0, nullptr)) != 0) return rc;
     if (mb.max_win <= 128 && !h->attn_simt)
       QASR_LAUNCH(h, "window_attention", att_flops, stream,
-                  launch_window_attention_tc(&h->tm_qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, h->head_rows, h->num_sms, stream));
+                  launch_window_attention_tc(&h->tm_qkv, h->attn_tile_rows, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, h->head_rows, h->num_sms, stream));
     else
       QASR_LAUNCH(h, "window_attention", att_flops, stream,
                   launch_window_attention(h->qkv, h->att, d_win, n_win, mb.max_win, d, c.encoder_attention_heads, h->head_rows, stream));
@@ -702,7 +703,8 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = make_tmap_rowmajor(&h->tm_ffn, h->ffn, mt, ffn, ffn, 128)) != 0) return rc;
   // head-major qkv (EpiQkv): [3][heads][mt][64] viewed as a [3 * heads * mt, 64] matrix for the attention kernel's TMA
   h->head_rows = static_cast<int>(mt);
-  if ((rc = make_tmap_rowmajor(&h->tm_qkv, h->qkv, 3LL * c.encoder_attention_heads * static_cast<long long>(mt), 64, 64, 128)) != 0) return rc;
+  h->attn_tile_rows = attention_tc_tile_rows(h->chunks_per_window * kTokPerChunk);
+  if ((rc = make_tmap_rowmajor(&h->tm_qkv, h->qkv, 3LL * c.encoder_attention_heads * static_cast<long long>(mt), 64, 64, h->attn_tile_rows)) != 0) return rc;
   // the tcgen05 attention multiplies V rows past a window's end by exact zeros: they must never hold NaN / Inf bit patterns
   QASR_CUDA_CHECK(cudaMemset(h->qkv, 0, mt * 3 * d * sizeof(bf16)));
   if (h->fp8) {
@@ -1303,11 +1305,12 @@ int debug_attention(const void* qkv, void* out, const int32_t* win_start_len_hos
   if (e == cudaSuccess) {
     if (tc) {
       CUtensorMap tm;
-      rc = make_tmap_rowmajor(&tm, hm, 3LL * heads * head_rows, 64, 64, 128);
+      const int tile_rows = attention_tc_tile_rows(max_win);
+      rc = make_tmap_rowmajor(&tm, hm, 3LL * heads * head_rows, 64, 64, tile_rows);
       int dev = 0, sms = kNumSMs;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (rc == 0) e = launch_window_attention_tc(&tm, static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, head_rows, sms, stream);
+      if (rc == 0) e = launch_window_attention_tc(&tm, tile_rows, static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, head_rows, sms, stream);
     } else {
       e = launch_window_attention(hm, static_cast<bf16*>(out), dwin, n_win, max_win, d, heads, head_rows, stream);
     }
