@@ -401,12 +401,130 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// conv1 on the tensor cores (product path).  The 9-tap, 1-input-channel convolution is a [pixels x 16] x [16 x channels]
+// product (taps 9..15 are zero), small enough for warp-level mma.sync.m16n8k16: one instruction replaces 1152 FFMAs, which
+// leaves the kernel with what it cannot avoid -- the erf-GELU, the two bf16 roundings and the 3 GB of stores.
+//   CTA  = one chunk x 26 output-column slots, mel tile (bf16) in shared memory
+//   warp = one block of 32 output channels (15 warps = 480 channels): its weight fragments (4 n-tiles) and biases stay in
+//          registers for the whole CTA; it walks the CTA's (column, 16-row block) pixel groups
+//   The n-columns of the four n-tiles are PERMUTED over the 32 channels (tile j, column 2t+e <-> channel 8t + 2j + e) so that
+//   the accumulator fragments of a thread are 8 CONSECUTIVE channels of its two rows: one 16-byte store per row and thread,
+//   64 contiguous bytes per row and quad -- full sectors without a shared-memory transpose.
+// ---------------------------------------------------------------------------------------------
+constexpr int C1M_COLS = 26;                   // column slots per CTA (52 / 2)
+constexpr int C1M_PITCH = 58;                  // bf16 elements per tile row: 53 frames used; 2 rows = 58 words = 26 mod 32 banks
+constexpr int C1M_TILE_H = 130;                // mel bins -1 .. 128
+constexpr int C1M_WARPS = 15;                  // 480 channels / 32
+constexpr int C1M_THREADS = C1M_WARPS * 32;
+
+template <typename MelT>
+__device__ __forceinline__ unsigned short mel_load_bf16_bits(const MelT* p);
+template <>
+__device__ __forceinline__ unsigned short mel_load_bf16_bits<float>(const float* p) {  // the .to(bf16) cast
+  return __bfloat16_as_ushort(__float2bfloat16_rn(__ldg(p)));
+}
+template <>
+__device__ __forceinline__ unsigned short mel_load_bf16_bits<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return *reinterpret_cast<const unsigned short*>(p);
+}
+
+template <typename MelT>
+__global__ void __launch_bounds__(C1M_THREADS, 2) conv1_mma_kernel(const MelT* __restrict__ mel, long long ld, const ChunkDesc* __restrict__ chunks,
+                                                                  const float* __restrict__ w, const float* __restrict__ bias,
+                                                                  __nv_bfloat16* __restrict__ act1) {
+  constexpr int channels = 480;
+  __shared__ __align__(16) unsigned short tile[C1M_TILE_H * C1M_PITCH];
+  const int chunk = blockIdx.x;
+  const int slot0 = blockIdx.y * C1M_COLS;
+  const ChunkDesc cd = chunks[chunk];
+  const int tid = threadIdx.x, lane = tid & 31, cb = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  // mel frames f = 2*(slot-1) - 1 + j for the slots of this CTA: f0 = 2*slot0 - 3
+  const int f0 = 2 * slot0 - 3;
+  for (int i = tid; i < C1M_TILE_H * C1M_PITCH; i += C1M_THREADS) {
+    const int r = i / C1M_PITCH, cc = i - r * C1M_PITCH;
+    const int bin = r - 1, f = f0 + cc;
+    unsigned short v = 0;
+    if (bin >= 0 && bin < 128 && f >= 0 && f < cd.valid && cc < 2 * C1M_COLS + 1) v = mel_load_bf16_bits<MelT>(mel + bin * ld + cd.mel_col0 + f);
+    tile[i] = v;
+  }
+
+  // weight fragments (B, "col" layout: b0 = {k = 2t, 2t+1}, b1 = {k = 2t+8, 2t+9} of column n = g) and the biases of the
+  // channels this thread's accumulators belong to
+  uint32_t b0[4], b1[4];
+  float bia[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ch = cb * 32 + 8 * (g >> 1) + 2 * j + (g & 1);
+    b0[j] = pack_bf16x2(__ldg(w + ch * 9 + 2 * t), __ldg(w + ch * 9 + 2 * t + 1));
+    b1[j] = t == 0 ? pack_bf16x2(__ldg(w + ch * 9 + 8), 0.f) : 0u;
+    bia[j][0] = __ldg(bias + cb * 32 + 8 * t + 2 * j);
+    bia[j][1] = __ldg(bias + cb * 32 + 8 * t + 2 * j + 1);
+  }
+  // tile offsets of this lane's two taps k = 2t, 2t+1 (k = 3 kh + kw) relative to (row 2h, column 2s)
+  const int offA = ((2 * t) / 3) * C1M_PITCH + (2 * t) % 3;
+  const int offB = ((2 * t + 1) / 3) * C1M_PITCH + (2 * t + 1) % 3;
+  constexpr int off8 = 2 * C1M_PITCH + 2;
+  __syncthreads();
+
+  for (int s = 0; s < C1M_COLS; ++s) {
+    const int slot = slot0 + s;
+    const int ow = slot - 1;  // output column of the chunk; slot 0 / 51 are padding
+    const bool live = ow >= 0 && ow < cd.w1;
+    __nv_bfloat16* dst = act1 + ((static_cast<long long>(chunk) * ACT1_PITCH + slot) * ACT1_H) * channels + cb * 32 + 8 * t;
+    if (!live) {
+#pragma unroll
+      for (int i = 0; i < ACT1_H / 8; ++i) *reinterpret_cast<uint4*>(dst + static_cast<long long>(i * 8 + g) * channels) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+#pragma unroll 1
+    for (int h0 = 0; h0 < ACT1_H; h0 += 16) {
+      // A fragment: pixel rows h0 + g and h0 + g + 8 of output column s; pixel (h, s) reads tile rows 2h .. 2h+2, columns 2s .. 2s+2
+      const unsigned short* p0 = tile + (2 * (h0 + g)) * C1M_PITCH + 2 * s;
+      const unsigned short* p1 = p0 + 16 * C1M_PITCH;
+      uint32_t a[4];
+      a[0] = static_cast<uint32_t>(p0[offA]) | (static_cast<uint32_t>(p0[offB]) << 16);
+      a[1] = static_cast<uint32_t>(p1[offA]) | (static_cast<uint32_t>(p1[offB]) << 16);
+      a[2] = t == 0 ? static_cast<uint32_t>(p0[off8]) : 0u;
+      a[3] = t == 0 ? static_cast<uint32_t>(p1[off8]) : 0u;
+      float c[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c[j][0] = bia[j][0]; c[j][1] = bia[j][1]; c[j][2] = bia[j][0]; c[j][3] = bia[j][1];
+        mma_bf16_16816(c[j], a, b0[j], b1[j]);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {  // row g, then row g + 8
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xr = bf16_round2(c[j][2 * half], c[j][2 * half + 1]);
+          o[j] = pack_bf16x2(gelu_erf(xr.x), gelu_erf(xr.y));
+        }
+        *reinterpret_cast<uint4*>(dst + static_cast<long long>(h0 + g + 8 * half) * channels) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, const ChunkDesc* chunks, int n_chunks, const float* w,
-                         const float* bias, int channels, __nv_bfloat16* act1, cudaStream_t stream) {
+                         const float* bias, int channels, __nv_bfloat16* act1, bool simt, cudaStream_t stream) {
   if (n_chunks == 0) return cudaSuccess;
   if (channels > 480 || (channels & 1)) return cudaErrorInvalidValue;
+  if (!simt) {
+    if (channels != 480) return cudaErrorInvalidValue;
+    dim3 grid(n_chunks, ACT1_PITCH / C1M_COLS);
+    if (mel_is_bf16)
+      conv1_mma_kernel<__nv_bfloat16><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, act1);
+    else
+      conv1_mma_kernel<float><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, act1);
+    return cudaGetLastError();
+  }
+  // checker (QASR_DEBUG_SIMT=1): the fp32 FFMA version
   dim3 grid(n_chunks, ACT1_PITCH / C1_COLS);
   constexpr int smem = 0;
   if (mel_is_bf16)

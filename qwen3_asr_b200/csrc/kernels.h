@@ -52,7 +52,7 @@ constexpr int ACT1_PITCH = 52;  // columns per chunk in conv1's output: [zero][5
 constexpr int ACT1_H = 64;
 cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, const ChunkDesc* chunks, int n_chunks,
                          const float* w /*[C][9]*/, const float* bias /*[C]*/, int channels,
-                         __nv_bfloat16* act1, cudaStream_t stream);
+                         __nv_bfloat16* act1, bool simt /*fp32 FFMA checker instead of the mma.sync kernel*/, cudaStream_t stream);
 
 // ---- FP8 dynamic quantisation (quant.cu) -----------------------------------------------------
 // x: bf16 [rows, k] (ld ldx) -> q: e4m3 [rows, k] (ld ldq bytes) + row_scale[rows].  per_row = false: one scale for

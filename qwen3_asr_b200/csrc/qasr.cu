@@ -382,7 +382,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   double att_flops = 0;
   for (const int2& w : mb.win) att_flops += 4.0 * w.y * w.y * d;
   QASR_LAUNCH(h, "conv1", px1 * kConvC * 18.0, stream,
-              launch_conv1(mel, mel_is_bf16, mel_ld, d_cd, nc, h->conv1_w, h->conv1_b, kConvC, h->act1, stream));
+              launch_conv1(mel, mel_is_bf16, mel_ld, d_cd, nc, h->conv1_w, h->conv1_b, kConvC, h->act1, h->simt, stream));
   {
     ConvArgs a{};
     a.tm_a = &h->tm_act1; a.tm_b = &h->tm_conv2_w;
