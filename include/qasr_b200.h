@@ -190,8 +190,8 @@ QASR_API int qasr_pool_set_weight(qasr_pool_t p, const char* name, const void* d
 QASR_API int qasr_pool_finalize(qasr_pool_t p);
 QASR_API size_t qasr_pool_workspace_bytes(qasr_pool_t p);
 /* qasr_submit_pcm_host across the pool.  Returns at once; token_lens_out [n_clips] and (optionally) clip_device_out
- * [n_clips] (the CUDA device each clip was sent to) are filled before it returns.  pcm_host, clip_offsets' data and
- * out_host must stay valid until qasr_pool_collect(ticket) returns; any number of batches may be in flight (each worker
+ * [n_clips] (the CUDA device each clip was sent to) are filled before it returns and not touched afterwards (clip_offsets
+ * is copied).  pcm_host and out_host must stay valid until qasr_pool_collect(ticket) returns; any number of batches may be in flight (each worker
  * keeps two on its GPU).  out_host: bf16 [sum tokens, output_dim] in clip order. */
 QASR_API int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                               int64_t out_capacity_tokens, int64_t* token_lens_out, int32_t* clip_device_out, uint64_t* ticket_out);

@@ -37,7 +37,6 @@ struct Shard {
   std::vector<int64_t> offsets;   // this shard's clip offsets (absolute sample indices into pcm_host)
   void* out_host = nullptr;
   int64_t out_capacity_tokens = 0;
-  int64_t* token_lens_out = nullptr;
   uint64_t handle_ticket = 0;
 };
 
@@ -103,7 +102,9 @@ void worker_main(qasr_pool_s* p, Worker* w) {
     }
     if (enqueue) {
       const int n = static_cast<int>(s.offsets.size()) - 1;
-      const int rc = qasr_submit_pcm_host(w->handle, s.pcm_host, s.offsets.data(), n, s.out_host, s.out_capacity_tokens, s.token_lens_out,
+      // token lengths were already reported by qasr_pool_submit itself: nothing the caller owns besides the PCM and output
+      // buffers is touched from this thread
+      const int rc = qasr_submit_pcm_host(w->handle, s.pcm_host, s.offsets.data(), n, s.out_host, s.out_capacity_tokens, nullptr,
                                           w->stream, &s.handle_ticket);
       if (rc != 0) {
         finish_shard(p, s, rc);
@@ -221,7 +222,6 @@ int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_o
     s.offsets.assign(clip_offsets + a, clip_offsets + b + 1);
     s.out_host = static_cast<char*>(out_host) + static_cast<size_t>(tok_off[a]) * p->output_dim * 2;
     s.out_capacity_tokens = tok_off[b] - tok_off[a];
-    s.token_lens_out = token_lens_out + a;
     shards.emplace_back(k, std::move(s));
   }
   batch->pending = static_cast<int>(shards.size());
