@@ -412,8 +412,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
 //   the accumulator fragments of a thread are 8 CONSECUTIVE channels of its two rows: one 16-byte store per row and thread,
 //   64 contiguous bytes per row and quad -- full sectors without a shared-memory transpose.
 // ---------------------------------------------------------------------------------------------
-constexpr int C1M_COLS = 26;                   // column slots per CTA (52 / 2)
-constexpr int C1M_PITCH = 58;                  // bf16 elements per tile row: 53 frames used; 2 rows = 58 words = 26 mod 32 banks
+constexpr int C1M_COLS = 26;                   // column slots per CTA at batch sizes that fill the GPU (52 / 2)
+constexpr int C1M_COLS_SMALL = 4;              // ... and for a handful of chunks (a WS window): 13 CTAs per chunk instead of 2
+constexpr int C1M_PITCH = 58;                  // bf16 elements per tile row: <= 53 frames used; 2 rows = 58 words = 26 mod 32 banks
 constexpr int C1M_TILE_H = 130;                // mel bins -1 .. 128
 constexpr int C1M_WARPS = 15;                  // 480 channels / 32
 constexpr int C1M_THREADS = C1M_WARPS * 32;
@@ -429,14 +430,14 @@ __device__ __forceinline__ unsigned short mel_load_bf16_bits<__nv_bfloat16>(cons
   return *reinterpret_cast<const unsigned short*>(p);
 }
 
-template <typename MelT>
+template <typename MelT, int COLS>
 __global__ void __launch_bounds__(C1M_THREADS, 2) conv1_mma_kernel(const MelT* __restrict__ mel, long long ld, const ChunkDesc* __restrict__ chunks,
                                                                   const float* __restrict__ w, const float* __restrict__ bias,
                                                                   __nv_bfloat16* __restrict__ act1) {
   constexpr int channels = 480;
   __shared__ __align__(16) unsigned short tile[C1M_TILE_H * C1M_PITCH];
   const int chunk = blockIdx.x;
-  const int slot0 = blockIdx.y * C1M_COLS;
+  const int slot0 = blockIdx.y * COLS;
   const ChunkDesc cd = chunks[chunk];
   const int tid = threadIdx.x, lane = tid & 31, cb = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(C1M_THREADS, 2) conv1_mma_kernel(const MelT* _
     const int r = i / C1M_PITCH, cc = i - r * C1M_PITCH;
     const int bin = r - 1, f = f0 + cc;
     unsigned short v = 0;
-    if (bin >= 0 && bin < 128 && f >= 0 && f < cd.valid && cc < 2 * C1M_COLS + 1) v = mel_load_bf16_bits<MelT>(mel + bin * ld + cd.mel_col0 + f);
+    if (bin >= 0 && bin < 128 && f >= 0 && f < cd.valid && cc < 2 * COLS + 1) v = mel_load_bf16_bits<MelT>(mel + bin * ld + cd.mel_col0 + f);
     tile[i] = v;
   }
 
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(C1M_THREADS, 2) conv1_mma_kernel(const MelT* _
   constexpr int off8 = 2 * C1M_PITCH + 2;
   __syncthreads();
 
-  for (int s = 0; s < C1M_COLS; ++s) {
+  for (int s = 0; s < COLS; ++s) {
     const int slot = slot0 + s;
     const int ow = slot - 1;  // output column of the chunk; slot 0 / 51 are padding
     const bool live = ow >= 0 && ow < cd.w1;
@@ -517,11 +518,20 @@ cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, con
   if (channels > 480 || (channels & 1)) return cudaErrorInvalidValue;
   if (!simt) {
     if (channels != 480) return cudaErrorInvalidValue;
-    dim3 grid(n_chunks, ACT1_PITCH / C1M_COLS);
-    if (mel_is_bf16)
-      conv1_mma_kernel<__nv_bfloat16><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, act1);
-    else
-      conv1_mma_kernel<float><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, act1);
+    static_assert(ACT1_PITCH % C1M_COLS == 0 && ACT1_PITCH % C1M_COLS_SMALL == 0, "column groups tile the 52 slots");
+    if (n_chunks * (ACT1_PITCH / C1M_COLS) >= 2 * kNumSMs) {
+      dim3 grid(n_chunks, ACT1_PITCH / C1M_COLS);
+      if (mel_is_bf16)
+        conv1_mma_kernel<__nv_bfloat16, C1M_COLS><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, act1);
+      else
+        conv1_mma_kernel<float, C1M_COLS><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, act1);
+    } else {  // few chunks: more, smaller CTAs (the weight fragments are reloaded per CTA, which is noise next to an idle GPU)
+      dim3 grid(n_chunks, ACT1_PITCH / C1M_COLS_SMALL);
+      if (mel_is_bf16)
+        conv1_mma_kernel<__nv_bfloat16, C1M_COLS_SMALL><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, act1);
+      else
+        conv1_mma_kernel<float, C1M_COLS_SMALL><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, act1);
+    }
     return cudaGetLastError();
   }
   // checker (QASR_DEBUG_SIMT=1): the fp32 FFMA version

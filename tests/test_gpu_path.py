@@ -507,3 +507,32 @@ def test_full_size_properties_1p7b():
         assert err <= HID_TOL, err
     finally:
         enc.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_encoder_fuzz_ragged_batches_vs_oracle(tiny, seed):
+    """Randomly shaped ragged batches (clip lengths from 1 frame-chunk fragments to several attention windows, lengths that
+    hit every tail-chunk / tail-window / odd-tile case) against the bf16-emulating oracle, and against a one-clip-per-call
+    run of the same kernels (bit-exact)."""
+    from oracle.signals import noise_clip, speech_like
+
+    cfg, w, enc = tiny
+    rng = np.random.default_rng(1000 + seed)
+    special = [201, 1600, 15999, 16000, 16160, 127999, 128000, 128160, 131200]      # samples: edges of frames / chunks / windows
+    n = int(rng.integers(3, 9))
+    lens = [int(rng.choice(special)) if rng.random() < 0.4 else int(rng.integers(201, 200000)) for _ in range(n)]
+    clips = [speech_like(m, 300 + 17 * seed + i) if i % 2 else noise_clip(m, 300 + 17 * seed + i) for i, m in enumerate(lens)]
+    out, toks = enc.encode_pcm(clips)
+    torch.cuda.synchronize()
+    assert [int(t) for t in toks] == [enc.token_len(m // 160) for m in lens]
+    mels = [_bf16_round(m) for m in _mels(enc, clips)]
+    ref, ref_toks = _oracle(cfg, w, [m for m in mels if m.shape[1] > 0], emulate_bf16=True)
+    assert sum(int(t) for t in toks) == ref.shape[0]
+    if ref.shape[0]:
+        assert range_rel(out.float().cpu().numpy(), ref.numpy()) <= HID_TOL
+    s = 0
+    for c, t in zip(clips, toks):
+        alone, _ = enc.encode_pcm([c])
+        torch.cuda.synchronize()
+        assert torch.equal(alone, out[s:s + int(t)]), (c.shape[0], int(t))
+        s += int(t)
