@@ -120,6 +120,15 @@ QASR_API int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* c
 QASR_API int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
                 void* out_dev, int64_t* token_lens_out, void* stream);
 
+/* qasr_encode whose last GEMM writes every encoder token straight into its row of the decoder's input embeddings: the
+ * fused form of `inputs_embeds.masked_scatter(audio_mask, audio_features)` (transformers modeling_qwen3_omni_moe.py:2135-2143,
+ * SURVEY.md section 8 row a15 / 8f-3) -- the [tokens, output_dim] intermediate and the scatter pass disappear.
+ *   embeds_dev         bf16 [rows, embeds_ld], embeds_ld >= output_dim (the decoder's hidden size), 16-byte aligned
+ *   token_rows_dev     DEVICE int64 [sum tokens]: row of embeds_dev for each encoder token, in clip-major token order
+ *                      (= the flattened positions where audio_mask is true) */
+QASR_API int qasr_encode_scatter(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
+                                 void* embeds_dev, int64_t embeds_ld, const int64_t* token_rows_dev, int64_t* token_lens_out, void* stream);
+
 /* Fused PCM -> log-mel -> encoder on the device (the mel stays in the handle's workspace). */
 QASR_API int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, void* out_dev,
                     int64_t* token_lens_out, void* stream);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "qasr_token_len": (C.c_int64, [C.c_int64]),
     "qasr_logmel": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P]),
     "qasr_encode": (C.c_int, [_P, _P, C.c_int, C.c_int64, _I64P, C.c_int, _P, _I64P, _P]),
+    "qasr_encode_scatter": (C.c_int, [_P, _P, C.c_int, C.c_int64, _I64P, C.c_int, _P, C.c_int64, _P, _I64P, _P]),
     "qasr_encode_pcm": (C.c_int, [_P, _P, _I64P, C.c_int, _P, _I64P, _P]),
     "qasr_encode_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P]),
     "qasr_submit_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P, C.POINTER(C.c_uint64)]),

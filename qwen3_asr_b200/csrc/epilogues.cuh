@@ -68,13 +68,17 @@ struct EpiLinear {
   const __nv_bfloat16* residual;   // [M, ldo] (may alias out) when RESIDUAL
   long long ldo;
   int m_valid, n_valid;
+  const long long* row_map = nullptr;  // optional: output row of GEMM row m (the fused scatter into the decoder's inputs_embeds)
   struct Prefetch { uint4 r; };
   static constexpr bool kScaled = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return n_valid; }
   __device__ __forceinline__ bool row_live(int) const { return true; }
   __device__ __forceinline__ float act(float v) const { return ACT == ACT_GELU ? gelu_erf(v) : v; }
-  __device__ __forceinline__ long long offset(int m, int n) const { return (m < m_valid && n < n_valid) ? m * ldo + n : -1; }
+  __device__ __forceinline__ long long offset(int m, int n) const {
+    if (m >= m_valid || n >= n_valid) return -1;
+    return (row_map != nullptr ? __ldg(row_map + m) : static_cast<long long>(m)) * ldo + n;
+  }
   __device__ __forceinline__ Prefetch prefetch(int, int, long long off) const {
     Prefetch p;
     if (RESIDUAL) p.r = *reinterpret_cast<const uint4*>(residual + off);

@@ -184,8 +184,9 @@ cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_
   const int kb = a.fp8 ? tc::block_k_elems<tc::K_E4M3>() : tc::BLOCK_K;
   if (a.k % kb != 0 || a.n % 16 != 0 || (!simt && (a.bn == 0 || a.n % a.bn != 0))) return cudaErrorInvalidValue;
   if (a.fp8 && (a.row_scale == nullptr || a.col_scale == nullptr)) return cudaErrorInvalidValue;
+  if (a.row_map != nullptr && a.epi != LIN_PLAIN) return cudaErrorInvalidValue;
   switch (a.epi) {
-    case LIN_PLAIN: return linear_kind(a, EpiLinear<ACT_NONE, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
+    case LIN_PLAIN: return linear_kind(a, EpiLinear<ACT_NONE, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n, a.row_map}, simt, num_sms, stream);
     case LIN_GELU: return linear_kind(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
     case LIN_RESIDUAL: return linear_kind(a, EpiLinear<ACT_NONE, true>{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, simt, num_sms, stream);
     case LIN_QKV: {

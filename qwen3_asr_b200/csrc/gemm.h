@@ -49,6 +49,7 @@ struct LinearArgs {
   const float* bias;           // [n] or nullptr
   const __nv_bfloat16* residual;  // LIN_RESIDUAL: [m, ldo]
   long long head_rows;         // LIN_QKV: token capacity of one (section, head) plane of the head-major output
+  const long long* row_map;    // LIN_PLAIN only, optional: device array, output row of each GEMM row (fused scatter)
   // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,
   // y = acc * row_scale[m] * col_scale[n] + bias
   int fp8;

@@ -343,8 +343,10 @@ struct MicroBatch {
   int max_win = 0;
 };
 
-int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long mel_ld, const MicroBatch& mb, bf16* out,
-                   cudaStream_t stream) {
+// out / out_ld / row_map: where proj2 writes.  Dense: out + token * out_ld.  Scatter (row_map != nullptr, device array indexed by the
+// micro-batch's token): out + row_map[token] * out_ld.
+int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long mel_ld, const MicroBatch& mb, bf16* out, long long out_ld,
+                   const long long* row_map, cudaStream_t stream) {
   const qasr_config_t& c = h->cfg;
   const int nc = static_cast<int>(mb.cd.size());
   const int ntok = mb.tokens;
@@ -424,8 +426,9 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   // one nn.Linear: (fp8: quantise the bf16 input first) GEMM with fused bias / GELU / residual epilogue
   // a_raw == nullptr: the producer (LayerNorm) has already left the quantised input and its row scales in h->a8 / h->a_scale
   auto linear = [&](const char* name, double flops, const CUtensorMap* tm_a, const bf16* a_raw, const LinearW& w, int epi, bf16* o,
-                    long long ldo, const bf16* residual) -> int {
+                    long long ldo, const bf16* residual, const long long* rmap = nullptr) -> int {
     LinearArgs la{};
+    la.row_map = rmap;
     la.tm_a = tm_a; la.tm_b = &w.tm; la.bn = w.bn; la.a = a_raw; la.lda = w.k; la.b = w.w; la.ldb = w.k;
     la.m = ntok; la.n = w.n; la.k = w.k; la.epi = epi; la.out = o; la.ldo = ldo; la.bias = w.b; la.residual = residual;
     la.head_rows = h->head_rows;
@@ -467,7 +470,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   // ---- output head
   if ((rc = layernorm(h->lnp_g, h->lnp_b)) != 0) return rc;
   if ((rc = linear("proj1_gemm", 2.0 * ntok * d * d, &h->tm_h, ln_out, h->proj1, LIN_GELU, h->att, d, nullptr)) != 0) return rc;
-  if ((rc = linear("proj2_gemm", 2.0 * ntok * d * c.output_dim, &h->tm_att, h->att, h->proj2, LIN_PLAIN, out, c.output_dim, nullptr)) != 0) return rc;
+  if ((rc = linear("proj2_gemm", 2.0 * ntok * d * c.output_dim, &h->tm_att, h->att, h->proj2, LIN_PLAIN, out, out_ld, nullptr, row_map)) != 0) return rc;
 
   QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
   st->in_flight = true;
@@ -806,8 +809,28 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   return 0;
 }
 
+namespace {
+int encode_impl(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips, void* out_dev,
+                int64_t out_ld, const int64_t* token_rows_dev, int64_t* token_lens_out, void* stream_v);
+}
+
 int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
                 void* out_dev, int64_t* token_lens_out, void* stream_v) {
+  return encode_impl(h, mel_dev, mel_dtype, mel_ld, feature_lens, n_clips, out_dev, h != nullptr ? h->cfg.output_dim : 0, nullptr, token_lens_out,
+                     stream_v);
+}
+
+int qasr_encode_scatter(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
+                        void* embeds_dev, int64_t embeds_ld, const int64_t* token_rows_dev, int64_t* token_lens_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && token_rows_dev != nullptr, "qasr_encode_scatter: bad argument");
+  QASR_REQUIRE(embeds_ld >= h->cfg.output_dim && embeds_ld % 8 == 0, "qasr_encode_scatter: embeds_ld must be >= output_dim and a multiple of 8");
+  QASR_REQUIRE((reinterpret_cast<uintptr_t>(embeds_dev) & 15) == 0, "qasr_encode_scatter: embeds_dev must be 16-byte aligned");
+  return encode_impl(h, mel_dev, mel_dtype, mel_ld, feature_lens, n_clips, embeds_dev, embeds_ld, token_rows_dev, token_lens_out, stream_v);
+}
+
+namespace {
+int encode_impl(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips, void* out_dev,
+                int64_t out_ld, const int64_t* token_rows_dev, int64_t* token_lens_out, void* stream_v) {
   QASR_REQUIRE(h != nullptr && feature_lens != nullptr && n_clips >= 0, "qasr_encode: bad argument");
   QASR_REQUIRE(h->finalized, "qasr_encode before qasr_finalize");
   QASR_REQUIRE(mel_dtype == QASR_F32 || mel_dtype == QASR_BF16, "qasr_encode: mel dtype must be f32 or bf16");
@@ -877,8 +900,12 @@ int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel
       ++ui;
     }
     QASR_REQUIRE(chunks > 0, "qasr_encode: a single attention window exceeds the micro-batch capacity");
-    const int rc = run_microbatch(h, mel_dev, mel_dtype == QASR_BF16, mel_ld, mb,
-                                  static_cast<bf16*>(out_dev) + tok_off * h->cfg.output_dim, stream);
+    static_assert(sizeof(long long) == sizeof(int64_t), "row maps are int64");
+    const int rc = token_rows_dev == nullptr
+                       ? run_microbatch(h, mel_dev, mel_dtype == QASR_BF16, mel_ld, mb, static_cast<bf16*>(out_dev) + tok_off * out_ld, out_ld,
+                                        nullptr, stream)
+                       : run_microbatch(h, mel_dev, mel_dtype == QASR_BF16, mel_ld, mb, static_cast<bf16*>(out_dev), out_ld,
+                                        reinterpret_cast<const long long*>(token_rows_dev) + tok_off, stream);
     if (rc != 0) return rc;
     tok_off += mb.tokens;
   }
@@ -886,6 +913,7 @@ int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel
   h->last_mel_ld = mel_ld;
   return 0;
 }
+}  // namespace
 
 int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, void* out_dev,
                     int64_t* token_lens_out, void* stream) {

@@ -195,6 +195,31 @@ class B200AudioEncoder:
         self.last_token_lens = toks
         return out
 
+    def encode_into(self, mel: torch.Tensor, feature_lens, inputs_embeds: torch.Tensor, audio_mask: torch.Tensor):
+        """Encode and write every audio token straight into its placeholder row of the decoder's ``inputs_embeds`` -- the fused
+        form of ``inputs_embeds.masked_scatter(audio_mask[..., None], audio_features)`` (modeling_qwen3_omni_moe.py:2135-2143).
+        ``inputs_embeds``: bf16 [..., hidden] on this device with hidden == output_dim; ``audio_mask``: bool [...] (one flag per
+        position, true at the audio placeholders, in the order the clips were given).  Returns the token lengths."""
+        assert mel.is_cuda and mel.dim() == 2 and mel.shape[0] == N_MELS and mel.stride(1) == 1
+        if mel.dtype not in (torch.float32, torch.bfloat16):
+            mel = mel.float()
+        assert inputs_embeds.is_cuda and inputs_embeds.dtype == torch.bfloat16 and inputs_embeds.is_contiguous()
+        assert inputs_embeds.shape[-1] == self.output_dim and tuple(audio_mask.shape) == tuple(inputs_embeds.shape[:-1])
+        flens = np.ascontiguousarray(np.asarray(torch.as_tensor(feature_lens).cpu()), dtype=np.int64).reshape(-1)
+        n = int(flens.shape[0])
+        total = int(sum(self.token_len(int(t)) for t in flens))
+        rows = torch.nonzero(audio_mask.reshape(-1).to(self.tdev), as_tuple=False).reshape(-1).to(torch.int64).contiguous()
+        if int(rows.numel()) != total:
+            raise QasrError(f"audio_mask marks {int(rows.numel())} positions but the clips produce {total} audio tokens")
+        toks = np.zeros(n, dtype=np.int64)
+        check(self.lib, self.lib.qasr_encode_scatter(self._h, C.c_void_p(mel.data_ptr()), _DTYPES[mel.dtype], int(mel.stride(0)),
+                                                     flens.ctypes.data_as(_lib._I64P), n, C.c_void_p(inputs_embeds.data_ptr()),
+                                                     int(inputs_embeds.shape[-1]), C.c_void_p(rows.data_ptr()),
+                                                     toks.ctypes.data_as(_lib._I64P), self._stream()),
+              "qasr_encode_scatter")
+        self._keep_rows = rows   # the kernels read it asynchronously on the stream
+        return toks
+
     def encode_pcm_packed(self, pcm: torch.Tensor, offsets: np.ndarray, out: torch.Tensor | None = None):
         assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)

@@ -536,3 +536,43 @@ def test_encoder_fuzz_ragged_batches_vs_oracle(tiny, seed):
         torch.cuda.synchronize()
         assert torch.equal(alone, out[s:s + int(t)]), (c.shape[0], int(t))
         s += int(t)
+
+
+def test_encode_into_equals_masked_scatter(tiny):
+    """qasr_encode_scatter: the last GEMM writes each audio token into its placeholder row of inputs_embeds -- bit-identical to
+    the reference's inputs_embeds.masked_scatter(audio_mask, audio_features) (modeling_qwen3_omni_moe.py:2135-2143), also when
+    the request is split into several micro-batches."""
+    from oracle import CONFIGS, make_weights
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import B200AudioEncoder, QasrError
+
+    cfg, w, enc = tiny
+    small = B200AudioEncoder(cfg, w, max_chunks=8)          # 8 chunks per micro-batch: the 3 clips below need several
+    try:
+        lens = [1234, 800, 90]
+        clips = [speech_like(t * 160, 900 + i) for i, t in enumerate(lens)]
+        mel, flens = small.logmel(clips)
+        feats = small.encode(mel, flens)
+        torch.cuda.synchronize()
+        toks = [small.token_len(int(t)) for t in flens]
+        # a [2, S, D] decoder input: text embeddings everywhere, audio placeholders in three runs (clip order)
+        S, D = 200, cfg.output_dim
+        g = torch.Generator(device="cpu").manual_seed(0)
+        embeds = torch.randn(2, S, D, generator=g).to(torch.bfloat16).cuda()
+        mask = torch.zeros(2, S, dtype=torch.bool)
+        mask[0, 5:5 + toks[0]] = True
+        mask[1, 0:toks[1]] = True
+        mask[1, 150:150 + toks[2]] = True
+        assert int(mask.sum()) == sum(toks) and max(5 + toks[0], 150 + toks[2]) <= S
+        want = embeds.clone().masked_scatter(mask.cuda()[..., None].expand_as(embeds), feats)
+        got = embeds.clone()
+        out_toks = small.encode_into(mel, flens, got, mask)
+        torch.cuda.synchronize()
+        assert out_toks.tolist() == toks
+        assert torch.equal(got, want)
+        bad = mask.clone()
+        bad[0, 0] = True
+        with pytest.raises(QasrError):
+            small.encode_into(mel, flens, got, bad)
+    finally:
+        small.close()
