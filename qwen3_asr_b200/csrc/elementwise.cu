@@ -545,6 +545,56 @@ cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, con
 }
 
 namespace {
+// (mean, rstd) of every row: what LayerNorm would normalise with (same two-pass fp32 arithmetic as layernorm_kernel), for the
+// Linears that have LayerNorm folded in (epilogues.cuh, LnFold).  One warp per row, nothing kept but the row: 48 warps per SM.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, int rows, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    const uint4 raw = col < d ? *reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * d + col) : make_uint4(0, 0, 0, 0);
+    float2 t;
+    t = unpack_bf16x2(raw.x); v[i][0] = t.x; v[i][1] = t.y;
+    t = unpack_bf16x2(raw.y); v[i][2] = t.x; v[i][3] = t.y;
+    t = unpack_bf16x2(raw.z); v[i][4] = t.x; v[i][5] = t.y;
+    t = unpack_bf16x2(raw.w); v[i][6] = t.x; v[i][7] = t.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += v[i][j];
+  }
+  const float inv_d = 1.0f / d;
+  const float mean = warp_sum(sum) * inv_d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; sq = fmaf(t, t, sq); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+}  // namespace
+
+cudaError_t launch_ln_stats(const __nv_bfloat16* x, float2* stats, int rows, int d, float eps, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;
+  const int grid = (rows + 7) / 8;
+  const int nv = (d + 255) / 256;
+  if (nv <= 1) ln_stats_kernel<1><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
+  else if (nv <= 2) ln_stats_kernel<2><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
+  else if (nv <= 4) ln_stats_kernel<4><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
+  else ln_stats_kernel<8><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
+  return cudaGetLastError();
+}
+
+namespace {
 template <bool FP8_OUT>
 cudaError_t launch_ln(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* out, uint8_t* q_out, float* row_scale,
                       int rows, int d, float eps, cudaStream_t stream) {

@@ -68,17 +68,14 @@ struct EpiLinear {
   const __nv_bfloat16* residual;   // [M, ldo] (may alias out) when RESIDUAL
   long long ldo;
   int m_valid, n_valid;
-  const long long* row_map = nullptr;  // optional: output row of GEMM row m (the fused scatter into the decoder's inputs_embeds)
   struct Prefetch { uint4 r; };
   static constexpr bool kScaled = false;
+  static constexpr bool kLnFold = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return n_valid; }
   __device__ __forceinline__ bool row_live(int) const { return true; }
   __device__ __forceinline__ float act(float v) const { return ACT == ACT_GELU ? gelu_erf(v) : v; }
-  __device__ __forceinline__ long long offset(int m, int n) const {
-    if (m >= m_valid || n >= n_valid) return -1;
-    return (row_map != nullptr ? __ldg(row_map + m) : static_cast<long long>(m)) * ldo + n;
-  }
+  __device__ __forceinline__ long long offset(int m, int n) const { return (m < m_valid && n < n_valid) ? m * ldo + n : -1; }
   __device__ __forceinline__ Prefetch prefetch(int, int, long long off) const {
     Prefetch p;
     if (RESIDUAL) p.r = *reinterpret_cast<const uint4*>(residual + off);
@@ -95,6 +92,16 @@ struct EpiLinear {
     } else {
       *reinterpret_cast<uint4*>(out + off) = y;
     }
+  }
+};
+
+// nn.Linear whose output rows are scattered: GEMM row m lands in row row_map[m] of `out` (the fused
+// inputs_embeds.masked_scatter of qasr_encode_scatter).  A separate type so that the hot residual / GELU epilogues carry no
+// run-time check (a nullable row map inside EpiLinear cost the K = 1024 out_proj GEMM 20 %).
+struct EpiLinearRows : EpiLinear<ACT_NONE, false> {
+  const long long* row_map;  // [M] device
+  __device__ __forceinline__ long long offset(int m, int n) const {
+    return (m < m_valid && n < n_valid) ? __ldg(row_map + m) * ldo + n : -1;
   }
 };
 
@@ -121,6 +128,19 @@ struct Scaled : Base {
   __device__ __forceinline__ float row_scale(int m) const { return m < this->m_valid ? __ldg(row_scale_p + m) : 0.f; }
 };
 
+// LayerNorm folded into the Linear that consumes it:  LN(x) W^T + b = rstd * (x (gamma . W)^T - mean * colsum) + (beta W^T + b),
+// colsum[n] = sum_k (gamma . W)[n, k].  The GEMM runs on the raw residual stream x with the pre-scaled weight; the epilogue
+// applies the row statistics: y = (acc - mean[m] * colsum[n]) * rstd[m] + bias'[n], then the base epilogue (rounding, activation,
+// layout) unchanged.  Saves the LayerNorm kernel's pass over the activation and one bf16 rounding point.
+template <class Base>
+struct LnFold : Base {
+  const float2* stats_p;    // [M] (mean, rstd) of the rows of x
+  const float* colsum_p;    // [N]
+  static constexpr bool kLnFold = true;
+  __device__ __forceinline__ const float* col_scale_ptr() const { return colsum_p; }
+  __device__ __forceinline__ float2 row_stats(int m) const { return m < this->m_valid ? __ldg(stats_p + m) : make_float2(0.f, 0.f); }
+};
+
 // Implicit-GEMM convolution epilogue: row m = (global output column g, output row h) with
 // g = chunk * slots + ow.  Writes bf16(gelu(bf16(acc + bias))) into the next layer's
 // [column][row][channel] layout at column chunk * out_pitch + out_off + ow; columns at or beyond
@@ -137,6 +157,7 @@ struct EpiConv {
   int n_chunks, c;         // c = channels (480)
   typedef NoPrefetch Prefetch;
   static constexpr bool kScaled = false;
+  static constexpr bool kLnFold = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return c; }
   __device__ __forceinline__ bool row_live(int m) const {
@@ -169,6 +190,7 @@ struct EpiConvOut {
   int d, m_valid;
   struct Prefetch { float4 a, b; };
   static constexpr bool kScaled = false;
+  static constexpr bool kLnFold = false;
   __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
   __device__ __forceinline__ int n_cols() const { return d; }
   __device__ __forceinline__ bool row_live(int) const { return true; }

@@ -95,8 +95,9 @@ template <int BN, int AMODE, int KIND, class Epi>
 cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc::GemmShape& shape, const Epi& epi, int num_sms,
                       cudaStream_t stream) {
   constexpr bool CTA2 = kGemmCta2;
-  constexpr int ST = tc::default_stages<BN, CTA2>();
-  using L = tc::SmemLayout<BN, ST, Epi::kScaled, CTA2>;
+  // LayerNorm-folded Linears double-buffer two per-column tables: one ring stage less pays for them
+  constexpr int ST = tc::default_stages<BN, CTA2>() - (Epi::kLnFold ? 1 : 0);
+  using L = tc::SmemLayout<BN, ST, Epi::kScaled, CTA2, Epi::kLnFold>;
   auto kern = tc::gemm_tc_kernel<BN, ST, AMODE, KIND, CTA2, Epi>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
   if (e != cudaSuccess) return e;
@@ -177,6 +178,15 @@ cudaError_t linear_kind(const LinearArgs& a, const Epi& e, bool simt, int num_sm
   return linear_dispatch<tc::K_BF16>(a, e, simt, num_sms, stream);
 }
 
+// LayerNorm-folded Linears exist in bf16 only and never run through the SIMT checker (handles in those modes keep the separate
+// LayerNorm kernel)
+template <class Epi>
+cudaError_t linear_ln(const LinearArgs& a, const Epi& e, bool simt, int num_sms, cudaStream_t stream) {
+  if (simt || a.fp8 || a.ln_colsum == nullptr) return cudaErrorNotSupported;
+  LnFold<Epi> le{e, a.ln_stats, a.ln_colsum};
+  return linear_dispatch<tc::K_BF16>(a, le, false, num_sms, stream);
+}
+
 }  // namespace
 
 cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_t stream) {
@@ -185,13 +195,19 @@ cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_
   if (a.k % kb != 0 || a.n % 16 != 0 || (!simt && (a.bn == 0 || a.n % a.bn != 0))) return cudaErrorInvalidValue;
   if (a.fp8 && (a.row_scale == nullptr || a.col_scale == nullptr)) return cudaErrorInvalidValue;
   if (a.row_map != nullptr && a.epi != LIN_PLAIN) return cudaErrorInvalidValue;
+  if (a.ln_stats != nullptr && a.epi != LIN_GELU && a.epi != LIN_QKV) return cudaErrorInvalidValue;
   switch (a.epi) {
-    case LIN_PLAIN: return linear_kind(a, EpiLinear<ACT_NONE, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n, a.row_map}, simt, num_sms, stream);
-    case LIN_GELU: return linear_kind(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
+    case LIN_PLAIN:
+      if (a.row_map != nullptr) return linear_kind(a, EpiLinearRows{{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, a.row_map}, simt, num_sms, stream);
+      return linear_kind(a, EpiLinear<ACT_NONE, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
+    case LIN_GELU:
+      if (a.ln_stats != nullptr) return linear_ln(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
+      return linear_kind(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
     case LIN_RESIDUAL: return linear_kind(a, EpiLinear<ACT_NONE, true>{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, simt, num_sms, stream);
     case LIN_QKV: {
       if (a.n % 64 != 0 || a.head_rows < a.m) return cudaErrorInvalidValue;
       EpiQkv e{{a.out, a.bias, nullptr, 0, a.m, a.n}, a.head_rows};
+      if (a.ln_stats != nullptr) return linear_ln(a, e, simt, num_sms, stream);
       return linear_kind(a, e, simt, num_sms, stream);
     }
     default: return cudaErrorInvalidValue;

@@ -50,6 +50,10 @@ struct LinearArgs {
   const __nv_bfloat16* residual;  // LIN_RESIDUAL: [m, ldo]
   long long head_rows;         // LIN_QKV: token capacity of one (section, head) plane of the head-major output
   const long long* row_map;    // LIN_PLAIN only, optional: device array, output row of each GEMM row (fused scatter)
+  // LayerNorm folded into this Linear (LIN_GELU / LIN_QKV, bf16 only): A is the raw residual stream, b the gamma-scaled weight,
+  // bias the beta-folded bias; the epilogue applies (acc - mean * colsum) * rstd
+  const float2* ln_stats;      // [m] (mean, rstd) or nullptr
+  const float* ln_colsum;      // [n]
   // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,
   // y = acc * row_scale[m] * col_scale[n] + bias
   int fp8;

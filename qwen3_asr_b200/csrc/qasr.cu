@@ -52,6 +52,7 @@ struct LinearW {
   uint8_t* w8 = nullptr;   // [n, k] e4m3 (fp8 mode)
   float* wscale = nullptr; // [n] weight scales (fp8 mode)
   float* b = nullptr;      // [n] or nullptr
+  float* colsum = nullptr; // [n] LayerNorm-folded Linears: column sums of the gamma-scaled bf16 weight
   int n = 0, k = 0, bn = 0;
   CUtensorMap tm;          // over w or w8
 };
@@ -100,6 +101,9 @@ struct qasr_handle_s {
   bool fp8 = false;         // QASR_FLAG_FP8: e4m3 x e4m3 Linears with dynamic activation scales (QUANTIZE=fp8)
   bool fp8_per_row = false; // QASR_FLAG_FP8_PER_ROW: per-row activation / per-output-channel weight scales (else per-tensor)
   bool simt = false;        // QASR_DEBUG_SIMT=1: run every GEMM through the SIMT checker kernel
+  bool ln_fold = false;     // LayerNorm folded into qkv / fc1 / proj1 (bf16 tcgen05 path; QASR_LN=unfused keeps the separate kernel)
+  float2* ln_stats = nullptr;  // [max tokens] (mean, rstd) of the residual stream's rows
+  CUtensorMap tm_x;
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
   int chunks_per_window = 8;
   int attn_tile_rows = 128;  // token rows of the attention kernel's TMA tiles (112 when every window fits)
@@ -278,12 +282,35 @@ int upload_bf16(qasr_handle_s* h, const float* src, size_t n, bf16** dst) {
 
 // nn.Linear [n, k] (+ bias) -> device weight (bf16, or e4m3 + scales in fp8 mode), f32 bias, TMA map with box rows = bn.
 // `modules`: number of nn.Linear modules stacked along n (3 for the fused q|k|v weight): each owns its per-tensor scale.
-int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, LinearW* out, int modules = 1) {
+// ln_g / ln_b (both or neither): fold the LayerNorm that feeds this Linear into it (handles with ln_fold): the device weight becomes
+// bf16(gamma[k] * bf16(w[n, k])), colsum[n] its row sums, and the bias absorbs beta: b'[n] = b[n] + sum_k beta[k] * bf16(w[n, k]).
+int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, LinearW* out, int modules = 1, const float* ln_g = nullptr,
+                const float* ln_b = nullptr) {
   out->n = n;
   out->k = k;
   out->bn = pick_bn(n);
   QASR_REQUIRE(out->bn != 0, "linear output width " + std::to_string(n) + " is not a multiple of 64");
   QASR_REQUIRE(k % 64 == 0, "linear input width " + std::to_string(k) + " is not a multiple of 64");
+  if (ln_g != nullptr && h->ln_fold) {
+    const size_t nk = static_cast<size_t>(n) * k;
+    std::vector<float> wf(nk), colsum(n), bias(n);
+    for (int r = 0; r < n; ++r) {
+      double cs = 0.0, bs = b != nullptr ? static_cast<double>(b[r]) : 0.0;
+      for (int c = 0; c < k; ++c) {
+        const float wb = __bfloat162float(__float2bfloat16_rn(w[static_cast<size_t>(r) * k + c]));
+        const float folded = __bfloat162float(__float2bfloat16_rn(wb * ln_g[c]));
+        wf[static_cast<size_t>(r) * k + c] = folded;
+        cs += folded;
+        bs += static_cast<double>(ln_b[c]) * wb;
+      }
+      colsum[r] = static_cast<float>(cs);
+      bias[r] = static_cast<float>(bs);
+    }
+    if (upload_f32(h, bias.data(), n, &out->b) != 0) return 2;
+    if (upload_f32(h, colsum.data(), n, &out->colsum) != 0) return 2;
+    if (upload_bf16(h, wf.data(), nk, &out->w) != 0) return 2;
+    return make_tmap_rowmajor(&out->tm, out->w, n, k, k, gemm_b_box_rows(out->bn));
+  }
   if (b != nullptr && upload_f32(h, b, n, &out->b) != 0) return 2;
   if (h->fp8) {
     QASR_REQUIRE(k % 128 == 0, "fp8 mode needs linear input widths that are multiples of 128, got " + std::to_string(k));
@@ -302,11 +329,17 @@ int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, 
   return make_tmap_rowmajor(&out->tm, out->w, n, k, k, gemm_b_box_rows(out->bn));
 }
 
-int load_linear(qasr_handle_s* h, const std::string& prefix, int n, int k, bool bias, LinearW* out) {
-  const HostTensor *w = nullptr, *b = nullptr;
+// ln_prefix: name of the LayerNorm module whose output this Linear consumes ("" = none) -- folded in on handles with ln_fold
+int load_linear(qasr_handle_s* h, const std::string& prefix, int n, int k, bool bias, LinearW* out, const std::string& ln_prefix = "") {
+  const HostTensor *w = nullptr, *b = nullptr, *g = nullptr, *be = nullptr;
   if (need_weight(h, prefix + ".weight", {n, k}, &w) != 0) return 1;
   if (bias && need_weight(h, prefix + ".bias", {n}, &b) != 0) return 1;
-  return make_linear(h, w->data.data(), bias ? b->data.data() : nullptr, n, k, out);
+  if (!ln_prefix.empty()) {
+    if (need_weight(h, ln_prefix + ".weight", {k}, &g) != 0) return 1;
+    if (need_weight(h, ln_prefix + ".bias", {k}, &be) != 0) return 1;
+  }
+  return make_linear(h, w->data.data(), bias ? b->data.data() : nullptr, n, k, out, 1, g != nullptr ? g->data.data() : nullptr,
+                     be != nullptr ? be->data.data() : nullptr);
 }
 
 int load_vec(qasr_handle_s* h, const std::string& name, int n, float** out) {
@@ -429,6 +462,12 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
                     long long ldo, const bf16* residual, const long long* rmap = nullptr) -> int {
     LinearArgs la{};
     la.row_map = rmap;
+    if (w.colsum != nullptr) {  // LayerNorm folded in: the operand is the residual stream itself, the epilogue applies the row statistics
+      la.ln_stats = h->ln_stats;
+      la.ln_colsum = w.colsum;
+      tm_a = &h->tm_x;
+      a_raw = h->x;
+    }
     la.tm_a = tm_a; la.tm_b = &w.tm; la.bn = w.bn; la.a = a_raw; la.lda = w.k; la.b = w.w; la.ldb = w.k;
     la.m = ntok; la.n = w.n; la.k = w.k; la.epi = epi; la.out = o; la.ldo = ldo; la.bias = w.b; la.residual = residual;
     la.head_rows = h->head_rows;
@@ -443,7 +482,9 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   // LayerNorm feeding a Linear: bf16 row to hbuf, or (fp8 per-row) straight to e4m3 + row scale -> returns the Linear's input
   const bool ln_fused_quant = h->fp8 && h->fp8_per_row;
   auto layernorm = [&](const float* g, const float* b) -> int {
-    if (ln_fused_quant)
+    if (h->ln_fold)
+      QASR_LAUNCH(h, "ln_stats", 0, stream, launch_ln_stats(h->x, h->ln_stats, ntok, d, 1e-5f, stream));
+    else if (ln_fused_quant)
       QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm_fp8(h->x, g, b, h->a8, h->a_scale, ntok, d, 1e-5f, stream));
     else
       QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm(h->x, g, b, h->hbuf, ntok, d, 1e-5f, stream));
@@ -533,6 +574,8 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
     delete h;
     return 1;
   }
+  e = std::getenv("QASR_LN");
+  h->ln_fold = !h->fp8 && !h->simt && !(e != nullptr && std::string(e) == "unfused");
   e = std::getenv("QASR_ATTENTION");
   h->attn_simt = e != nullptr && std::string(e) == "mma_sync";
   e = std::getenv("QASR_DEBUG_KEEP");
@@ -662,10 +705,13 @@ int qasr_finalize(qasr_handle_t h) {
       std::memcpy(b.data(), bq->data.data(), sizeof(float) * d);
       std::memcpy(b.data() + d, bk->data.data(), sizeof(float) * d);
       std::memcpy(b.data() + 2 * d, bv->data.data(), sizeof(float) * d);
-      if ((rc = make_linear(h, w.data(), b.data(), 3 * d, d, &L.qkv, 3)) != 0) return rc;
+      const HostTensor *g1, *b1;
+      if ((rc = need_weight(h, p + "self_attn_layer_norm.weight", {d}, &g1)) != 0) return rc;
+      if ((rc = need_weight(h, p + "self_attn_layer_norm.bias", {d}, &b1)) != 0) return rc;
+      if ((rc = make_linear(h, w.data(), b.data(), 3 * d, d, &L.qkv, 3, g1->data.data(), b1->data.data())) != 0) return rc;
     }
     if ((rc = load_linear(h, p + "self_attn.out_proj", d, d, true, &L.out)) != 0) return rc;
-    if ((rc = load_linear(h, p + "fc1", ffn, d, true, &L.fc1)) != 0) return rc;
+    if ((rc = load_linear(h, p + "fc1", ffn, d, true, &L.fc1, p + "final_layer_norm")) != 0) return rc;
     if ((rc = load_linear(h, p + "fc2", d, ffn, true, &L.fc2)) != 0) return rc;
     if ((rc = load_vec(h, p + "self_attn_layer_norm.weight", d, &L.ln1_g)) != 0) return rc;
     if ((rc = load_vec(h, p + "self_attn_layer_norm.bias", d, &L.ln1_b)) != 0) return rc;
@@ -674,7 +720,7 @@ int qasr_finalize(qasr_handle_t h) {
   }
   if ((rc = load_vec(h, "ln_post.weight", d, &h->lnp_g)) != 0) return rc;
   if ((rc = load_vec(h, "ln_post.bias", d, &h->lnp_b)) != 0) return rc;
-  if ((rc = load_linear(h, "proj1", d, d, true, &h->proj1)) != 0) return rc;
+  if ((rc = load_linear(h, "proj1", d, d, true, &h->proj1, "ln_post")) != 0) return rc;
   if ((rc = load_linear(h, "proj2", c.output_dim, d, true, &h->proj2)) != 0) return rc;
   h->staged.clear();
 
@@ -689,6 +735,7 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->act3), act3_elems * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->x), mt * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->hbuf), mt * d * sizeof(bf16))) != 0) return rc;
+  if (h->ln_fold && (rc = dev_alloc(h, reinterpret_cast<void**>(&h->ln_stats), mt * sizeof(float2))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->qkv), mt * 3 * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->att), mt * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->ffn), mt * ffn * sizeof(bf16))) != 0) return rc;
@@ -702,6 +749,7 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = make_tmap_conv(&h->tm_act2, h->act2, static_cast<long long>(mc) * 26, 32, kConvC, 16, 8)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_act3, h->act3, static_cast<long long>(mc) * kTokPerChunk, 16 * kConvC, 16 * kConvC, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_h, h->hbuf, mt, d, d, 128)) != 0) return rc;
+  if ((rc = make_tmap_rowmajor(&h->tm_x, h->x, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_att, h->att, mt, d, d, 128)) != 0) return rc;
   if ((rc = make_tmap_rowmajor(&h->tm_ffn, h->ffn, mt, ffn, ffn, 128)) != 0) return rc;
   // head-major qkv (EpiQkv): [3][heads][mt][64] viewed as a [3 * heads * mt, 64] matrix for the attention kernel's TMA

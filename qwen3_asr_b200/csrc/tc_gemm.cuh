@@ -269,7 +269,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 
 // SCALED (fp8 kinds): bias and column-scale tables are single-buffered (an extra epilogue barrier per tile keeps a fast
 // warp from overwriting them) -- with 4 stages of 48 KB and 32 KB of staging there is no room for two copies of both.
-template <int BN, int STAGES, bool SCALED = false, bool CTA2 = false>
+template <int BN, int STAGES, bool SCALED = false, bool CTA2 = false, bool LNFOLD = false>
 struct SmemLayout {
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;   // weight rows staged by this CTA (the pair's other CTA stages the rest)
   static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
@@ -277,8 +277,8 @@ struct SmemLayout {
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;               // [kEpiWarps][32 rows][128 B]
   static constexpr int TAB_BUFS = SCALED ? 1 : 2;
   static constexpr int BIAS_OFFSET = STAGING_OFFSET + kEpiWarps * kStagingBytes;  // float [TAB_BUFS][256]
-  static constexpr int SCALE_OFFSET = BIAS_OFFSET + TAB_BUFS * 256 * 4;           // float [256] column scales (SCALED only)
-  static constexpr int BAR_OFFSET = SCALE_OFFSET + (SCALED ? 256 * 4 : 0);
+  static constexpr int SCALE_OFFSET = BIAS_OFFSET + TAB_BUFS * 256 * 4;           // float [TAB_BUFS][256] column scales (fp8) / column sums (LnFold)
+  static constexpr int BAR_OFFSET = SCALE_OFFSET + ((SCALED || LNFOLD) ? TAB_BUFS * 256 * 4 : 0);
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -309,7 +309,7 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 template <int BN, int STAGES, int AMODE, int KIND, bool CTA2, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape shape, Epi epi) {
-  using L = SmemLayout<BN, STAGES, Epi::kScaled, CTA2>;
+  using L = SmemLayout<BN, STAGES, Epi::kScaled, CTA2, Epi::kLnFold>;
   static_assert(!CTA2 || BN % 16 == 0, "UMMA N for M=256 must be a multiple of 16; each CTA stages BN / 2 rows (whole 8-row swizzle atoms)");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(BN <= kAccStride, "an accumulator stage is kAccStride TMEM columns");
@@ -469,10 +469,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float b = 0.f;
         if (et < BN && bp != nullptr && n < epi.n_cols()) b = __ldg(bp + n);
         if (et < 256) bias_s[tab * 256 + et] = b;
-        if constexpr (Epi::kScaled) {
+        if constexpr (Epi::kScaled || Epi::kLnFold) {  // per-column table: fp8 weight scales / LayerNorm-fold column sums
           float cs = 0.f;
           if (et < BN && n < epi.n_cols()) cs = __ldg(epi.col_scale_ptr() + n);
-          if (et < 256) scale_s[et] = cs;
+          if (et < 256) scale_s[tab * 256 + et] = cs;
         }
       }
       named_bar_sync(1, kEpiThreads);
@@ -482,6 +482,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool live = epi.row_live(row0 + lane);
       float row_scale = 1.f;
       if constexpr (Epi::kScaled) row_scale = epi.row_scale(row0 + lane);
+      float2 ln = make_float2(0.f, 1.f);  // (rstd * mean, rstd) of this thread's row
+      if constexpr (Epi::kLnFold) {
+        ln = epi.row_stats(row0 + lane);
+        ln.x *= ln.y;
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
 #pragma unroll 1
       for (int p = pw; p < NP; p += kEpiWarps / 4) {
@@ -505,7 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (g * 16 < ncols) tmem_ld16(taddr + c0 + g * 16, v + g * 16);
         tmem_ld_wait();
         const float* bs = bias_s + tab * 256 + c0;
-        const float* ss = scale_s + c0;
+        const float* ss = scale_s + tab * 256 + c0;
 #pragma unroll
         for (int j = 0; j < kPanel / 8; ++j) {
           if (j * 8 < ncols) {
@@ -522,10 +527,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int e = 0; e < 8; ++e) acc[e] *= row_scale * sc[e];
             }
+            float pre_act[8];  // the module output before its bf16 rounding
+            if constexpr (Epi::kLnFold) {  // rstd * acc + (bias' - rstd * mean * colsum[n]): two FMAs per output
+              const float4 s0 = *reinterpret_cast<const float4*>(ss + j * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(ss + j * 8 + 4);
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pre_act[e] = fmaf(acc[e], ln.y, fmaf(-ln.x, sc[e], bb[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pre_act[e] = acc[e] + bb[e];
+            }
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
-              const float2 r = bf16_round2(acc[e] + bb[e], acc[e + 1] + bb[e + 1]);
+              const float2 r = bf16_round2(pre_act[e], pre_act[e + 1]);
               o[e] = live ? epi.act(r.x) : 0.f;
               o[e + 1] = live ? epi.act(r.y) : 0.f;
             }
