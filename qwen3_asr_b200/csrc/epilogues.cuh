@@ -71,9 +71,11 @@ struct EpiLinear {
   struct Prefetch { uint4 r; };
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
+  static constexpr bool kRowStats = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return n_valid; }
   __device__ __forceinline__ bool row_live(int) const { return true; }
+  __device__ __forceinline__ int stats_row(int m) const { return m < m_valid ? m : -1; }
   __device__ __forceinline__ float act(float v) const { return ACT == ACT_GELU ? gelu_erf(v) : v; }
   __device__ __forceinline__ long long offset(int m, int n) const { return (m < m_valid && n < n_valid) ? m * ldo + n : -1; }
   __device__ __forceinline__ Prefetch prefetch(int, int, long long off) const {
@@ -81,16 +83,20 @@ struct EpiLinear {
     if (RESIDUAL) p.r = *reinterpret_cast<const uint4*>(residual + off);
     return p;
   }
-  __device__ __forceinline__ void finish(long long off, const uint4& y, const Prefetch& p) const {
+  // stores and returns the 8 final bf16 values
+  __device__ __forceinline__ uint4 finish(long long off, const uint4& y, const Prefetch& p) const {
     if (RESIDUAL) {
       float a[8], r[8];
       unpack8(y, a);
       unpack8(p.r, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += r[j];
-      *reinterpret_cast<uint4*>(out + off) = pack8(a);
+      const uint4 v = pack8(a);
+      *reinterpret_cast<uint4*>(out + off) = v;
+      return v;
     } else {
       *reinterpret_cast<uint4*>(out + off) = y;
+      return y;
     }
   }
 };
@@ -158,6 +164,7 @@ struct EpiConv {
   typedef NoPrefetch Prefetch;
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
+  static constexpr bool kRowStats = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return c; }
   __device__ __forceinline__ bool row_live(int m) const {
@@ -175,8 +182,9 @@ struct EpiConv {
     return (col * hc + h) * c + n;
   }
   __device__ __forceinline__ Prefetch prefetch(int, int, long long) const { return Prefetch(); }
-  __device__ __forceinline__ void finish(long long off, const uint4& y, const Prefetch&) const {
+  __device__ __forceinline__ uint4 finish(long long off, const uint4& y, const Prefetch&) const {
     *reinterpret_cast<uint4*>(out + off) = y;
+    return y;
   }
 };
 
@@ -191,6 +199,8 @@ struct EpiConvOut {
   struct Prefetch { float4 a, b; };
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
+  static constexpr bool kRowStats = false;
+  __device__ __forceinline__ int stats_row(int m) const { return m < m_valid ? __ldg(row_token + m) : -1; }
   __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
   __device__ __forceinline__ int n_cols() const { return d; }
   __device__ __forceinline__ bool row_live(int) const { return true; }
@@ -207,13 +217,25 @@ struct EpiConvOut {
     r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     return r;
   }
-  __device__ __forceinline__ void finish(long long off, const uint4& y, const Prefetch& p) const {
+  __device__ __forceinline__ uint4 finish(long long off, const uint4& y, const Prefetch& p) const {
     float a[8];
     unpack8(y, a);
     a[0] += p.a.x; a[1] += p.a.y; a[2] += p.a.z; a[3] += p.a.w;
     a[4] += p.b.x; a[5] += p.b.y; a[6] += p.b.z; a[7] += p.b.w;
-    *reinterpret_cast<uint4*>(out + off) = pack8(a);
+    const uint4 v = pack8(a);
+    *reinterpret_cast<uint4*>(out + off) = v;
+    return v;
   }
+};
+
+// The epilogues that write the residual stream (conv_out, out_proj, fc2) can also leave what the NEXT LayerNorm needs: per row and
+// 32-column panel the sum and the sum of squares of the bf16 values just stored, in fixed slots part[row][panel] (deterministic:
+// no atomics).  ln_stats_finalize_kernel turns the d / 32 partials of a row into (mean, rstd) for the LnFold<> consumer.
+template <class Base>
+struct RowStats : Base {
+  float2* part;      // [rows][n_panels]
+  int n_panels;      // d / 32
+  static constexpr bool kRowStats = true;
 };
 
 }  // namespace qasr

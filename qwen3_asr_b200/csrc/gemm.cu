@@ -203,7 +203,13 @@ cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_
     case LIN_GELU:
       if (a.ln_stats != nullptr) return linear_ln(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
       return linear_kind(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
-    case LIN_RESIDUAL: return linear_kind(a, EpiLinear<ACT_NONE, true>{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, simt, num_sms, stream);
+    case LIN_RESIDUAL:
+      if (a.stats_part != nullptr) {
+        if (simt || a.fp8 || a.n % 64 != 0) return cudaErrorNotSupported;
+        RowStats<EpiLinear<ACT_NONE, true>> e{{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, a.stats_part, a.n / 32};
+        return linear_dispatch<tc::K_BF16>(a, e, false, num_sms, stream);
+      }
+      return linear_kind(a, EpiLinear<ACT_NONE, true>{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, simt, num_sms, stream);
     case LIN_QKV: {
       if (a.n % 64 != 0 || a.head_rows < a.m) return cudaErrorInvalidValue;
       EpiQkv e{{a.out, a.bias, nullptr, 0, a.m, a.n}, a.head_rows};
@@ -264,6 +270,10 @@ cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStre
     if (a.row_scale == nullptr || a.col_scale == nullptr) return cudaErrorInvalidValue;
     Scaled<EpiConvOut> se{e, a.row_scale, a.col_scale};
     return conv_out_dispatch<tc::K_E4M3>(a, se, num_sms, stream);
+  }
+  if (a.stats_part != nullptr) {
+    RowStats<EpiConvOut> re{e, a.stats_part, a.d / 32};
+    return conv_out_dispatch<tc::K_BF16>(a, re, num_sms, stream);
   }
   return conv_out_dispatch<tc::K_BF16>(a, e, num_sms, stream);
 }

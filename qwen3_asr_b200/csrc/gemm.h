@@ -54,6 +54,8 @@ struct LinearArgs {
   // bias the beta-folded bias; the epilogue applies (acc - mean * colsum) * rstd
   const float2* ln_stats;      // [m] (mean, rstd) or nullptr
   const float* ln_colsum;      // [n]
+  // LIN_RESIDUAL, bf16 only, optional: also leave per-row / per-32-column-panel (sum, sum of squares) of the stored values
+  float2* stats_part;          // [m][n / 32] or nullptr
   // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,
   // y = acc * row_scale[m] * col_scale[n] + bias
   int fp8;
@@ -96,6 +98,7 @@ struct ConvOutArgs {
   int fp8;                     // as in LinearArgs
   const float* row_scale;
   const float* col_scale;
+  float2* stats_part;          // optional (bf16 only): [tokens][d / 32] partial LayerNorm statistics of the rows written
 };
 cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStream_t stream);
 

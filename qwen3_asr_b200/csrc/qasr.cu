@@ -103,6 +103,8 @@ struct qasr_handle_s {
   bool simt = false;        // QASR_DEBUG_SIMT=1: run every GEMM through the SIMT checker kernel
   bool ln_fold = false;     // LayerNorm folded into qkv / fc1 / proj1 (bf16 tcgen05 path; QASR_LN=unfused keeps the separate kernel)
   float2* ln_stats = nullptr;  // [max tokens] (mean, rstd) of the residual stream's rows
+  float2* ln_part = nullptr;   // [max tokens][d / 32] partial sums left by the residual epilogues (QASR_LN=stats_kernel: unused)
+  bool ln_epi_stats = false;   // row statistics come from the producing GEMM's epilogue instead of a pass over x
   CUtensorMap tm_x;
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
   int chunks_per_window = 8;
@@ -446,6 +448,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     a.tm_a = &h->tm_act3; a.tm_b = &h->conv_out.tm; a.bn = h->conv_out.bn;
     a.a = h->act3; a.b = h->conv_out.w; a.m = nc * kTokPerChunk; a.d = d; a.k = 16 * kConvC;
     a.pe = h->pe; a.row_token = d_rt; a.tok_per_chunk = kTokPerChunk; a.out = h->x;
+    if (h->ln_epi_stats) a.stats_part = h->ln_part;
     if (h->fp8) {
       QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(h->act3, nc * kTokPerChunk, 16 * kConvC));
       a.tm_a = &h->tm_a8_conv; a.fp8 = 1; a.row_scale = h->a_scale; a.col_scale = h->conv_out.wscale;
@@ -462,6 +465,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
                     long long ldo, const bf16* residual, const long long* rmap = nullptr) -> int {
     LinearArgs la{};
     la.row_map = rmap;
+    if (epi == LIN_RESIDUAL && h->ln_epi_stats) la.stats_part = h->ln_part;  // every residual GEMM writes x: the next LayerNorm's partials
     if (w.colsum != nullptr) {  // LayerNorm folded in: the operand is the residual stream itself, the epilogue applies the row statistics
       la.ln_stats = h->ln_stats;
       la.ln_colsum = w.colsum;
@@ -482,7 +486,9 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   // LayerNorm feeding a Linear: bf16 row to hbuf, or (fp8 per-row) straight to e4m3 + row scale -> returns the Linear's input
   const bool ln_fused_quant = h->fp8 && h->fp8_per_row;
   auto layernorm = [&](const float* g, const float* b) -> int {
-    if (h->ln_fold)
+    if (h->ln_epi_stats)
+      QASR_LAUNCH(h, "ln_stats", 0, stream, launch_ln_stats_finalize(h->ln_part, d / 32, h->ln_stats, ntok, d, 1e-5f, stream));
+    else if (h->ln_fold)
       QASR_LAUNCH(h, "ln_stats", 0, stream, launch_ln_stats(h->x, h->ln_stats, ntok, d, 1e-5f, stream));
     else if (ln_fused_quant)
       QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm_fp8(h->x, g, b, h->a8, h->a_scale, ntok, d, 1e-5f, stream));
@@ -576,6 +582,10 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   }
   e = std::getenv("QASR_LN");
   h->ln_fold = !h->fp8 && !h->simt && !(e != nullptr && std::string(e) == "unfused");
+  // QASR_LN=epilogue_stats: the residual epilogues leave per-panel partial sums and a finalize kernel replaces the pass over x.
+  // Measured slower (12.38 vs 12.14 ms per step): any extra launch between two cluster GEMMs costs ~8 us whatever it does, and the
+  // residual epilogues pay 0.2 ms for the partials -- kept as an experiment switch, off by default.
+  h->ln_epi_stats = h->ln_fold && cfg->d_model % 64 == 0 && e != nullptr && std::string(e) == "epilogue_stats";
   e = std::getenv("QASR_ATTENTION");
   h->attn_simt = e != nullptr && std::string(e) == "mma_sync";
   e = std::getenv("QASR_DEBUG_KEEP");
@@ -736,6 +746,7 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->x), mt * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->hbuf), mt * d * sizeof(bf16))) != 0) return rc;
   if (h->ln_fold && (rc = dev_alloc(h, reinterpret_cast<void**>(&h->ln_stats), mt * sizeof(float2))) != 0) return rc;
+  if (h->ln_epi_stats && (rc = dev_alloc(h, reinterpret_cast<void**>(&h->ln_part), mt * (d / 32) * sizeof(float2))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->qkv), mt * 3 * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->att), mt * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->ffn), mt * ffn * sizeof(bf16))) != 0) return rc;

@@ -557,10 +557,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // phase B: each instruction moves eight complete 64-byte row segments
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (offs[i] >= 0) {
+          if constexpr (!Epi::kRowStats) {
+            if (offs[i] >= 0) {
+              const int r = i * 8 + sub;
+              const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
+              epi.finish(offs[i], sv, pre[i]);
+            }
+          } else {
+            // ... and leaves the row's partial LayerNorm statistics of this 32-column panel (sum, sum of squares of the stored bf16
+            // values): the four lanes of a row add up through two shuffles, lane ch == 0 writes the fixed slot part[row][panel]
             const int r = i * 8 + sub;
-            const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
-            epi.finish(offs[i], sv, pre[i]);
+            float s1 = 0.f, s2 = 0.f;
+            if (offs[i] >= 0) {
+              const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
+              const uint4 fin = epi.finish(offs[i], sv, pre[i]);
+              const float2 a = unpack_bf16x2(fin.x), b = unpack_bf16x2(fin.y), c = unpack_bf16x2(fin.z), d2 = unpack_bf16x2(fin.w);
+              s1 = ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d2.x + d2.y));
+              s2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c.x, c.x, fmaf(c.y, c.y, fmaf(d2.x, d2.x, d2.y * d2.y)))))));
+            }
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            if (ch == 0) {
+              const int srow = epi.stats_row(row0 + r);
+              if (srow >= 0) epi.part[static_cast<long long>(srow) * epi.n_panels + ((n_blk * BN + c0) >> 5)] = make_float2(s1, s2);
+            }
           }
         }
         __syncwarp();
