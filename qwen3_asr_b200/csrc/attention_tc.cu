@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __restrict__ win, int n_win, int heads, int d, int head_rows,
                     __nv_bfloat16* __restrict__ out, float scale_log2e) {
   constexpr int AT_STAGES = AtCfg<TR>::STAGES, AT_STAGE_BYTES = AtCfg<TR>::STAGE_BYTES, AT_TILE_BYTES = AtCfg<TR>::TILE_BYTES;
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_STAGES * AT_STAGE_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES] TMA -> MMA: Q, K, V of the stage have landed
@@ -117,6 +118,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // the prologue overlapped the QKV GEMM's tail; its output is read from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -346,11 +348,13 @@ cudaError_t launch_window_attention_tc(const CUtensorMap* tm_qkv, int tile_rows,
   if (tile_rows == 112) {
     e = cudaFuncSetAttribute(attention_tc_kernel<112>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<112>::SMEM);
     if (e != cudaSuccess) return e;
-    attention_tc_kernel<112><<<grid, AT_THREADS, AtCfg<112>::SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, head_rows, out, scale_log2e);
+    return launch_pdl(attention_tc_kernel<112>, dim3(grid), dim3(AT_THREADS), AtCfg<112>::SMEM, stream, 1, *tm_qkv, win, n_win, heads, d, head_rows, out,
+                      scale_log2e);
   } else {
     e = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<128>::SMEM);
     if (e != cudaSuccess) return e;
-    attention_tc_kernel<128><<<grid, AT_THREADS, AtCfg<128>::SMEM, stream>>>(*tm_qkv, win, n_win, heads, d, head_rows, out, scale_log2e);
+    return launch_pdl(attention_tc_kernel<128>, dim3(grid), dim3(AT_THREADS), AtCfg<128>::SMEM, stream, 1, *tm_qkv, win, n_win, heads, d, head_rows, out,
+                      scale_log2e);
   }
   return cudaGetLastError();
 }

@@ -113,4 +113,41 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch --------------------------------------------------------------
+// The step is a chain of ~176 dependent kernels; between two of them the GPU otherwise idles for the launch latency and the
+// next kernel's prologue (barrier init, TMEM allocation, cluster sync, descriptor prefetch).  Kernels on the chain call
+// pdl_launch_dependents() first (the next grid may be scheduled onto SMs as they drain) and pdl_wait() before they touch global
+// memory (it returns once the previous grid has completed and its writes are visible), and are launched with launch_pdl().
+// Both device calls are no-ops for a kernel launched without the attribute.  QASR_PDL=0 disables the attribute (A/B).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // qasr.cu
+
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, unsigned cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attrs[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = cluster_x;
+    attrs[n].val.clusterDim.y = 1;
+    attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = attrs;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace qasr

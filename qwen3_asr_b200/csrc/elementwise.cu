@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2) layernorm_kernel(const __nv_
                                                                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                                   uint8_t* __restrict__ q_out, float* __restrict__ row_scale,
                                                                   int rows, int d, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * LN_WARPS;
   int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -549,6 +551,8 @@ namespace {
 // Linears that have LayerNorm folded in (epilogues.cuh, LnFold).  One warp per row, nothing kept but the row: 48 warps per SM.
 template <int NV>
 __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, int rows, int d, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -621,11 +625,10 @@ cudaError_t launch_ln_stats(const __nv_bfloat16* x, float2* stats, int rows, int
   if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;
   const int grid = (rows + 7) / 8;
   const int nv = (d + 255) / 256;
-  if (nv <= 1) ln_stats_kernel<1><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
-  else if (nv <= 2) ln_stats_kernel<2><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
-  else if (nv <= 4) ln_stats_kernel<4><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
-  else ln_stats_kernel<8><<<grid, 256, 0, stream>>>(x, stats, rows, d, eps);
-  return cudaGetLastError();
+  if (nv <= 1) return launch_pdl(ln_stats_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, d, eps);
+  if (nv <= 2) return launch_pdl(ln_stats_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, d, eps);
+  if (nv <= 4) return launch_pdl(ln_stats_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, d, eps);
+  return launch_pdl(ln_stats_kernel<8>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, d, eps);
 }
 
 namespace {
@@ -635,11 +638,11 @@ cudaError_t launch_ln(const __nv_bfloat16* x, const float* gamma, const float* b
   // ~5 rows per warp at the C2 batch (12480 rows): enough rows to amortise the gamma/beta registers, enough warps to fill the chip
   const int grid = std::max(1, std::min((rows + LN_WARPS - 1) / LN_WARPS, 2 * kNumSMs));
   const int nv = (d + 255) / 256;
-  if (nv <= 1) layernorm_kernel<1, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
-  else if (nv <= 2) layernorm_kernel<2, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
-  else if (nv <= 4) layernorm_kernel<4, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
-  else layernorm_kernel<8, FP8_OUT><<<grid, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, out, q_out, row_scale, rows, d, eps);
-  return cudaGetLastError();
+  const dim3 g(grid), b(LN_WARPS * 32);
+  if (nv <= 1) return launch_pdl(layernorm_kernel<1, FP8_OUT>, g, b, 0, stream, 1, x, gamma, beta, out, q_out, row_scale, rows, d, eps);
+  if (nv <= 2) return launch_pdl(layernorm_kernel<2, FP8_OUT>, g, b, 0, stream, 1, x, gamma, beta, out, q_out, row_scale, rows, d, eps);
+  if (nv <= 4) return launch_pdl(layernorm_kernel<4, FP8_OUT>, g, b, 0, stream, 1, x, gamma, beta, out, q_out, row_scale, rows, d, eps);
+  return launch_pdl(layernorm_kernel<8, FP8_OUT>, g, b, 0, stream, 1, x, gamma, beta, out, q_out, row_scale, rows, d, eps);
 }
 }  // namespace
 

@@ -109,22 +109,22 @@ cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc
   } else {
     // persistent CTA pairs: as many 2-CTA clusters as the device can keep resident at once (one CTA per SM; a GPC with an
     // odd number of free SMs leaves one idle), never more than there are 256-row tiles
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.blockDim = dim3(tc::kThreads);
-    cfg.dynamicSmemBytes = L::TOTAL;
-    cfg.stream = stream;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
     static thread_local int max_clusters_cached[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     int max_clusters = dev < 64 ? max_clusters_cached[dev] : 0;
     if (max_clusters == 0) {
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.blockDim = dim3(tc::kThreads);
+      cfg.dynamicSmemBytes = L::TOTAL;
+      cfg.stream = stream;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
       cfg.gridDim = dim3(2 * (num_sms / 2));
       e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
       if (e != cudaSuccess) return e;
@@ -133,8 +133,7 @@ cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc
       if (dev < 64) max_clusters_cached[dev] = max_clusters;
     }
     const int tiles = ((shape.m_tiles + 1) / 2) * shape.n_tiles;
-    cfg.gridDim = dim3(2 * std::min(tiles, max_clusters));
-    return cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, shape, epi);
+    return launch_pdl(kern, dim3(2 * std::min(tiles, max_clusters)), dim3(tc::kThreads), L::TOTAL, stream, 2, tm_a, tm_b, shape, epi);
   }
 }
 

@@ -25,6 +25,13 @@ namespace {
 thread_local std::string g_last_error;
 }
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("QASR_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 }  // namespace qasr
 
 using namespace qasr;

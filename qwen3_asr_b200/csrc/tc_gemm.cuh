@@ -316,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(KIND == K_BF16 || AMODE == A_LINEAR, "the implicit-GEMM convolutions stay bf16 (torchao quantises nn.Linear only)");
   constexpr int KB_ELEMS = block_k_elems<KIND>();
 
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned stage bases
     if (threadIdx.x == 0) printf("qasr tc_gemm: dynamic shared memory is not 1024-byte aligned\n");
@@ -360,6 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
