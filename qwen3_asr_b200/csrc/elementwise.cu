@@ -593,6 +593,8 @@ __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __
                                                                 int rows, float inv_d, float eps) {
   // one warp per row, one panel per lane (d <= 2048: at most two rounds): a coalesced 256-byte read, then a butterfly whose
   // summation order is fixed by the lane ids
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -616,8 +618,7 @@ __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __
 cudaError_t launch_ln_stats_finalize(const float2* part, int n_panels, float2* stats, int rows, int d, float eps, cudaStream_t stream) {
   if (rows == 0) return cudaSuccess;
   if (n_panels * 32 != d) return cudaErrorInvalidValue;
-  ln_stats_finalize_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(part, n_panels, stats, rows, 1.0f / d, eps);
-  return cudaGetLastError();
+  return launch_pdl(ln_stats_finalize_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, 1, part, n_panels, stats, rows, 1.0f / d, eps);
 }
 
 cudaError_t launch_ln_stats(const __nv_bfloat16* x, float2* stats, int rows, int d, float eps, cudaStream_t stream) {
