@@ -28,8 +28,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # DRAM traffic measured once with ncu --set full (profiles/): the bench itself never runs under a profiler
-NCU_GEMM_DRAM_BYTES_PER_STEP = (4.099626 + 0.725013 + 0.796719 + 0.178766 + 0.240916 + 0.022367 + 24 * (
-    0.032017 + 0.027598 + 0.053372 + 0.000814 + 0.034128 + 0.051728 + 0.138113 + 0.013067)) * 1e9
+NCU_GEMM_DRAM_BYTES_PER_STEP = (3.192950 + 0.724703 + 0.782233 + 0.177196 + 0.241311 + 0.023039 + 24 * (
+    0.032128 + 0.027506 + 0.053372 + 0.000543 + 0.034240 + 0.053047 + 0.137746 + 0.013343)) * 1e9
 NCU_MEL_DRAM_BYTES_PER_LAUNCH = (497.989120 + 389.929216) * 1e6
 
 METRIC = "audio-sec encoded/sec (mel+encoder, 1.7B)"
@@ -331,7 +331,7 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of the family's 101 launches of one step (conv2 3.80 GB, conv3 0.95 GB,
             # conv_out 0.24 GB, per layer qkv 55 MB + out_proj 54 MB + fc1 81 MB + fc2 146 MB), ncu --set full, divided by 101
             "traffic": NCU_GEMM_DRAM_BYTES_PER_STEP / 101.0,
-            "traffic_source": "profiles/r01k_gemm_raw_summary.txt (one ncu --set full capture of each kernel of the family, C2 batch)",
+            "traffic_source": "profiles/r01p_gemm_raw_summary.txt (one ncu --set full capture of each kernel of the family, C2 batch)",
         }
         kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                        "tflops": (v["work"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and k != "logmel" and v["work"] > 0 else None}
