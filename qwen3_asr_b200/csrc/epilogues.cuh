@@ -143,8 +143,19 @@ struct LnFold : Base {
   const float2* stats_p;    // [M] (mean, rstd) of the rows of x
   const float* colsum_p;    // [N]
   static constexpr bool kLnFold = true;
+  static constexpr bool kLnPart = false;
   __device__ __forceinline__ const float* col_scale_ptr() const { return colsum_p; }
   __device__ __forceinline__ float2 row_stats(int m) const { return m < this->m_valid ? __ldg(stats_p + m) : make_float2(0.f, 0.f); }
+};
+// ... with the row statistics finalised INSIDE the consuming GEMM: the producers' residual epilogues (RowStats<>) left per-panel
+// (sum, sum of squares) partials; the GEMM kernel's two otherwise idle warps reduce the partials of the tile's 128 rows into a
+// shared-memory table while the tile's MMAs run.  No statistics kernel, no extra launch.
+template <class Base>
+struct LnFoldPart : LnFold<Base> {
+  const float2* part_p;     // [M][n_panels]
+  int n_panels;             // K / 32 (<= 64)
+  float inv_d, eps;
+  static constexpr bool kLnPart = true;
 };
 
 // Implicit-GEMM convolution epilogue: row m = (global output column g, output row h) with

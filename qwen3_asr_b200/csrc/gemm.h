@@ -54,6 +54,8 @@ struct LinearArgs {
   // bias the beta-folded bias; the epilogue applies (acc - mean * colsum) * rstd
   const float2* ln_stats;      // [m] (mean, rstd) or nullptr
   const float* ln_colsum;      // [n]
+  const float2* ln_part;       // alternative to ln_stats: [m][k / 32] per-panel (sum, sum of squares) left by the producer's RowStats<>
+                               // epilogue; the kernel's idle warps finalise them per tile
   // LIN_RESIDUAL, bf16 only, optional: also leave per-row / per-32-column-panel (sum, sum of squares) of the stored values
   float2* stats_part;          // [m][n / 32] or nullptr
   // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,

@@ -474,7 +474,8 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     la.row_map = rmap;
     if (epi == LIN_RESIDUAL && h->ln_epi_stats) la.stats_part = h->ln_part;  // every residual GEMM writes x: the next LayerNorm's partials
     if (w.colsum != nullptr) {  // LayerNorm folded in: the operand is the residual stream itself, the epilogue applies the row statistics
-      la.ln_stats = h->ln_stats;
+      if (h->ln_epi_stats) la.ln_part = h->ln_part;
+      else la.ln_stats = h->ln_stats;
       la.ln_colsum = w.colsum;
       tm_a = &h->tm_x;
       a_raw = h->x;
@@ -493,9 +494,8 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   // LayerNorm feeding a Linear: bf16 row to hbuf, or (fp8 per-row) straight to e4m3 + row scale -> returns the Linear's input
   const bool ln_fused_quant = h->fp8 && h->fp8_per_row;
   auto layernorm = [&](const float* g, const float* b) -> int {
-    if (h->ln_epi_stats)
-      QASR_LAUNCH(h, "ln_stats", 0, stream, launch_ln_stats_finalize(h->ln_part, d / 32, h->ln_stats, ntok, d, 1e-5f, stream));
-    else if (h->ln_fold)
+    if (h->ln_epi_stats) return 0;  // the consuming GEMM finalises the partials the last residual epilogue left: nothing to launch
+    if (h->ln_fold)
       QASR_LAUNCH(h, "ln_stats", 0, stream, launch_ln_stats(h->x, h->ln_stats, ntok, d, 1e-5f, stream));
     else if (ln_fused_quant)
       QASR_LAUNCH(h, "layernorm", 0, stream, launch_layernorm_fp8(h->x, g, b, h->a8, h->a_scale, ntok, d, 1e-5f, stream));
@@ -589,9 +589,9 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   }
   e = std::getenv("QASR_LN");
   h->ln_fold = !h->fp8 && !h->simt && !(e != nullptr && std::string(e) == "unfused");
-  // QASR_LN=epilogue_stats: the residual epilogues leave per-panel partial sums and a finalize kernel replaces the pass over x.
-  // Measured slower (12.38 vs 12.14 ms per step): any extra launch between two cluster GEMMs costs ~8 us whatever it does, and the
-  // residual epilogues pay 0.2 ms for the partials -- kept as an experiment switch, off by default.
+  // QASR_LN=epilogue_stats: the residual epilogues leave per-panel partial sums (RowStats<>) and the consuming GEMM's idle warps
+  // finalise them per tile (LnFoldPart<>): no statistics kernel at all.  Parity-green but measured no faster (12.1 vs 12.0 ms per
+  // step: what the removed pass saves, the epilogues pay) -- kept as an experiment switch, off by default.
   h->ln_epi_stats = h->ln_fold && cfg->d_model % 64 == 0 && e != nullptr && std::string(e) == "epilogue_stats";
   e = std::getenv("QASR_ATTENTION");
   h->attn_simt = e != nullptr && std::string(e) == "mma_sync";

@@ -106,6 +106,8 @@ QASR_DEFINE_MBAR_WAIT(wait_smem_empty)  // TMA producer: stage freed by the MMAs
 QASR_DEFINE_MBAR_WAIT(wait_smem_full)   // MMA issuer: TMA bytes of the stage have landed
 QASR_DEFINE_MBAR_WAIT(wait_tmem_empty)  // MMA issuer: epilogue has drained the accumulator stage
 QASR_DEFINE_MBAR_WAIT(wait_tmem_full)   // epilogue: the tile's last MMA has completed
+QASR_DEFINE_MBAR_WAIT(wait_stats_full)  // epilogue: the tile's row statistics are in the smem table (LnFoldPart)
+QASR_DEFINE_MBAR_WAIT(wait_stats_empty) // statistics warps: the table slot has been read
 #undef QASR_DEFINE_MBAR_WAIT
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -278,8 +280,9 @@ struct SmemLayout {
   static constexpr int TAB_BUFS = SCALED ? 1 : 2;
   static constexpr int BIAS_OFFSET = STAGING_OFFSET + kEpiWarps * kStagingBytes;  // float [TAB_BUFS][256]
   static constexpr int SCALE_OFFSET = BIAS_OFFSET + TAB_BUFS * 256 * 4;           // float [TAB_BUFS][256] column scales (fp8) / column sums (LnFold)
-  static constexpr int BAR_OFFSET = SCALE_OFFSET + ((SCALED || LNFOLD) ? TAB_BUFS * 256 * 4 : 0);
-  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int STAT_OFFSET = SCALE_OFFSET + ((SCALED || LNFOLD) ? TAB_BUFS * 256 * 4 : 0);  // float2 [2][128] row statistics (LnFoldPart)
+  static constexpr int BAR_OFFSET = STAT_OFFSET + (LNFOLD ? 2 * BLOCK_M * 8 : 0);
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 4;  // + stats_full[2], stats_empty[2] (LnFoldPart)
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
@@ -327,6 +330,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + STAGES;            // [STAGES] MMA -> TMA
   uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [2] MMA -> epilogue
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
+  uint64_t* stats_full_bar = bars + 2 * STAGES + 4;  // [2] statistics warps -> epilogue (LnFoldPart)
+  uint64_t* stats_empty_bar = bars + 2 * STAGES + 6; // [2] epilogue -> statistics warps
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -349,6 +354,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], (CTA2 ? 2 : 1) * kEpiWarps);  // one elected lane of each epilogue warp (of both CTAs)
+      mbar_init(&stats_full_bar[i], 2);
+      mbar_init(&stats_empty_bar[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -447,7 +454,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp < kEpiWarp0) {
+    // ===================== row statistics (warps 2, 3; LnFoldPart only) =====================
+    if constexpr (Epi::kLnFold) {
+      if constexpr (Epi::kLnPart) if (warp >= 2) {
+        float2* stat_s = reinterpret_cast<float2*>(smem + L::STAT_OFFSET);
+        const int sw = warp - 2;  // rows sw * 64 .. + 63 of the CTA's 128
+        int iter = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
+          const int m_blk = CTA2 ? 2 * (tile / shape.n_tiles) + rank : tile / shape.n_tiles;
+          const int as = iter & 1;
+          wait_stats_empty(&stats_empty_bar[as], ((iter >> 1) & 1) ^ 1);
+          // lane = row (two rows per lane): 2 x n_panels / 2 independent 16-byte loads per lane in flight, sums in registers, fixed
+          // order.  (A warp-per-row butterfly is a chain of dependent L2 round trips -- it took longer than the tile's MMAs.)
+          const int row0 = m_blk * BLOCK_M + sw * 64;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int row = row0 + hh * 32 + lane;
+            float s1 = 0.f, s2 = 0.f;
+            if (row < epi.m_valid) {
+              const float4* p = reinterpret_cast<const float4*>(epi.part_p + static_cast<long long>(row) * epi.n_panels);
+#pragma unroll 8
+              for (int i = 0; i < epi.n_panels / 2; ++i) {
+                const float4 v = __ldg(p + i);
+                s1 += v.x; s2 += v.y;
+                s1 += v.z; s2 += v.w;
+              }
+            }
+            const float mean = s1 * epi.inv_d;
+            const float var = fmaxf(fmaf(-mean, mean, s2 * epi.inv_d), 0.f);
+            const float rstd = rsqrtf(var + epi.eps);
+            stat_s[as * BLOCK_M + sw * 64 + hh * 32 + lane] = make_float2(mean * rstd, rstd);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stats_full_bar[as]);  // release: the table writes above are visible to the waiting epilogue warps
+        }
+      }
+    }
+  } else {
     // ===================== epilogue =====================
     const int ew = warp - kEpiWarp0;
     const int q = ew & 3;       // == warp % 4: the TMEM lane quarter this warp may read
@@ -486,8 +530,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (Epi::kScaled) row_scale = epi.row_scale(row0 + lane);
       float2 ln = make_float2(0.f, 1.f);  // (rstd * mean, rstd) of this thread's row
       if constexpr (Epi::kLnFold) {
-        ln = epi.row_stats(row0 + lane);
-        ln.x *= ln.y;
+        if constexpr (Epi::kLnPart) {
+          wait_stats_full(&stats_full_bar[as], aphase);
+          ln = reinterpret_cast<const float2*>(smem + L::STAT_OFFSET)[as * BLOCK_M + q * 32 + lane];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stats_empty_bar[as]);  // the row's statistics are in registers: the table slot may be refilled
+        } else {
+          ln = epi.row_stats(row0 + lane);
+          ln.x *= ln.y;
+        }
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
 #pragma unroll 1
