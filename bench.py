@@ -194,6 +194,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    if local_rank == 0:
+        from qwen3_asr_b200.build import build as build_lib
+
+        build_lib()  # no-op when the in-tree libqasr_b200.so is newer than its sources
+    if dist is not None:
+        dist.barrier()  # nobody loads the library while local rank 0 may be (re)linking it
+
     from qwen3_asr_b200 import B200AudioEncoder
     from qwen3_asr_b200.synth import model_config, random_weights, speech_like
 
