@@ -435,10 +435,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint64_t da = desc0 + static_cast<uint64_t>((stage * L::STAGE_BYTES) >> 4);
         const uint64_t db = da + static_cast<uint64_t>(A_STAGE_BYTES >> 4);
+        // implicit-GEMM convolutions: a tap's 480 channels are 7.5 k-blocks; the last block of every tap holds 32 real channels and
+        // 32 zero-padded ones -- its second half is skipped (two of four MMAs), 6.25 % of the convolution's tensor work
+        const bool half_block = AMODE == A_CONV && (kb % shape.kb_per_tap) == shape.kb_per_tap - 1;
         if (elect_one()) {
           if constexpr (CTA2) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K_BYTES / 32; ++k)
+              if (!(half_block && k >= BLOCK_K_BYTES / 64))
               umma_pair<KIND>(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage]);
             if (kb == shape.num_kb - 1) umma_commit_pair(&tmem_full_bar[as]);
