@@ -8,16 +8,18 @@
 //   * conv_out (K5): A is conv3's output viewed as [chunk*13, 16*480].
 // B is always an nn.Linear-style [N,K] row-major (K-major) weight.
 //
-// Roles (640 threads, 1 CTA per SM, grid = #SMs):
+// Roles (640 threads, 1 CTA per SM, grid = the number of co-resident CTA pairs x 2):
 //   warp 0 lane 0 : TMA producer   -- cp.async.bulk.tensor into a kStages-deep 128B-swizzled ring
-//   warp 1 lane 0 : MMA issuer     -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage
+//   warp 1 lane 0 : MMA issuer     -- tcgen05.mma (cta_group::2: M=256 over the pair, leader CTA only), N=BN, K=16 x4 per stage
 //   warp 2        : TMEM allocator -- 512 columns = two accumulator stages
+//   warps 2, 3    : (LnFoldPart epilogues only) reduce the LayerNorm partial sums of the tile's rows into a smem table
 //   warps 4..19   : epilogue       -- four warps per TMEM lane quarter (a GELU epilogue on 8 warps took longer than the
 //                                     K = 1024 main loop of its tile), 32-column panels: tcgen05.ld -> bias (from
 //                                     smem) / activation -> bf16 -> swizzled smem staging -> coalesced 64-byte row
 //                                     segments to global (+ residual / positional addend, prefetched)
 // Pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) mbarriers, so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// epilogue of tile i overlaps the MMAs of tile i+1.  The kernel takes part in programmatic dependent launch (common.cuh):
+// its prologue runs while the previous kernel of the chain drains.
 //
 // CTA2 = true (the product configuration): the two CTAs of a 2-CTA cluster (one TPC) work on one 256 x BN tile with
 // tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and only HALF of the B tile (BN / 2 weight rows); the
