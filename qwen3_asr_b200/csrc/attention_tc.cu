@@ -14,8 +14,9 @@
 //   warp 2        TMEM allocation: 4 slots x 128 columns.  A slot holds S (<= 128 fp32 columns); P (bf16 pairs) overwrites its
 //                 first 64 columns as the softmax proceeds, and O (64 fp32 columns) is accumulated into columns 64..127 --
 //                 the upper half of S, dead once the whole row has been read -- so four items fit where two did
-//   warps 4-19    four softmax warpgroups (thread = query row), item i served by warpgroup i % 4: tcgen05.ld S -> mask -> max ->
-//                 exp2 -> row sum -> bf16 P back into the S columns (tcgen05.st) -> after the second MMA, O / sum -> bf16 -> HBM
+//   warps 4-11    two softmax warpgroups (thread = query row), item i served by warpgroup i % 2 in slot i % 4: ONE tcgen05.ld sweep
+//                 of the S row into registers -> mask -> max -> exp2 -> row sum -> bf16 P back into the S columns (tcgen05.st) ->
+//                 after the second MMA, O / sum -> bf16 -> HBM
 // An item's softmax is a latency chain (TMEM round trips, 100+ dependent MUFU / FMNMX per row), so throughput comes from the
 // number of items in flight: four warpgroups, QK^T issued two items ahead of PV, and a 5-stage TMA ring (tiles of 112 rows
 // when every window fits, as with the checkpoints' 104-token windows).
@@ -29,8 +30,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int AT_SLOTS = 4;                       // TMEM slots == softmax warpgroups == items in the softmax stage at once
-constexpr int AT_THREADS = (4 + 4 * AT_SLOTS) * 32;  // 640
+constexpr int AT_SLOTS = 4;                       // TMEM slots: Q K^T runs up to four items ahead
+constexpr int AT_WGS = 2;                         // softmax warpgroups: few enough threads (384) that a whole S row fits in registers
+constexpr int AT_THREADS = (4 + 4 * AT_WGS) * 32;
 constexpr int AT_HD = 64;
 constexpr int AT_ROWS = 128;                      // query rows of the MMA (TMEM lanes); window length <= 128
 constexpr int AT_SLOT_COLS = 128;                 // TMEM: S in columns 0..127, P aliases 0..63, O aliases 64..127
@@ -195,103 +197,81 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
     for (int j = it >= AT_LOOKAHEAD ? it - AT_LOOKAHEAD : 0; j < it; ++j) issue_pv(j, static_cast<int>(blockIdx.x) + j * step);
   } else if (warp >= 4) {
     // ===================== softmax + output warpgroups =====================
-    const int wg = (warp - 4) >> 2;            // 0 .. AT_SLOTS-1: this warpgroup serves items whose slot == wg
+    const int wg = (warp - 4) >> 2;            // 0 .. AT_WGS-1: this warpgroup serves items it % AT_WGS == wg (slot it % AT_SLOTS)
     const int q = warp & 3;                    // TMEM lane quarter of this warp
     const int row = q * 32 + lane;             // query row == TMEM lane
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      if (it % AT_SLOTS != wg) continue;
+      if (it % AT_WGS != wg) continue;
+      const int slot = it % AT_SLOTS;
       const uint32_t ph = (it / AT_SLOTS) & 1;
       const int w = item / heads, h = item - w * heads;
       const int2 wd = __ldg(&win[w]);
       const int wl = wd.y;
       const int n16 = (wl + 15) >> 4;
-      const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(wg * AT_SLOT_COLS);
+      const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * AT_SLOT_COLS);
 
-      at_wait(&s_full[wg], ph);
+      at_wait(&s_full[slot], ph);
       tc_fence_after();
-      // Two passes over the S row (max, then exp), each walking 32-column batches with the NEXT batch's tcgen05.ld already in
-      // flight while the current one is processed, so TMEM latency is exposed once per pass rather than once per 16 columns.
+      // ONE sweep over the S row: all (<= 128) scores of the row into registers, then max, exp, sum from registers.  TMEM reads run
+      // at 64 B/clk/SM and were the largest single cost of the two-pass version (S read twice: 146 KB per item -> 89 KB).
       // Only the last 16-key granule can hold keys past the window's end.
       const int tail = wl - (n16 - 1) * 16;  // live keys in the last granule, 1..16
-      uint32_t buf[2][32];
-      auto load_batch = [&](int b) {  // granules 2b and 2b+1
-        tmem_ld16(t_s + b * 32, buf[b & 1]);
-        if (2 * b + 1 < n16) tmem_ld16(t_s + b * 32 + 16, buf[b & 1] + 16);
-      };
+      // (The granules are spelled out by macro: as loops over a 2-D register array the front end demoted the array to local memory.)
+      constexpr int NG = TR / 16;  // key granules a window of this kernel instance can have: 7 (112-row tiles) or 8
+      uint32_t v0[16], v1[16], v2[16], v3[16], v4[16], v5[16], v6[16], v7[16];
+      tmem_ld16(t_s + 0, v0);   // unconditional: columns past the window's end are loaded and ignored
+      tmem_ld16(t_s + 16, v1);
+      tmem_ld16(t_s + 32, v2);
+      tmem_ld16(t_s + 48, v3);
+      tmem_ld16(t_s + 64, v4);
+      tmem_ld16(t_s + 80, v5);
+      tmem_ld16(t_s + 96, v6);
+      if constexpr (NG > 7) tmem_ld16(t_s + 112, v7);
+      tmem_ld_wait();
       float mx0 = -INFINITY, mx1 = -INFINITY;
-      load_batch(0);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        if (2 * b < n16) {
-          tmem_ld_wait();
-          if (2 * (b + 1) < n16) load_batch(b + 1);
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int g = 2 * b + hh;
-            const uint32_t* v = buf[b & 1] + hh * 16;
-            if (g < n16 - 1) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                mx0 = fmaxf(mx0, __uint_as_float(v[j]));
-                mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
-              }
-            } else if (g == n16 - 1) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) mx0 = fmaxf(mx0, j < tail ? __uint_as_float(v[j]) : -INFINITY);
-            }
-          }
-        }
-      }
-      // p = exp2((s - max) * scale), row sum in fp32, bf16 pairs back into the slot's first columns
+#define AT_MAX_GRANULE(G, V)                                                                        \
+  if ((G) < n16 - 1) {                                                                             \
+    _Pragma("unroll") for (int j = 0; j < 16; j += 2) {                                            \
+      mx0 = fmaxf(mx0, __uint_as_float(V[j]));                                                     \
+      mx1 = fmaxf(mx1, __uint_as_float(V[j + 1]));                                                 \
+    }                                                                                              \
+  } else if ((G) == n16 - 1) {                                                                     \
+    _Pragma("unroll") for (int j = 0; j < 16; ++j) mx0 = fmaxf(mx0, j < tail ? __uint_as_float(V[j]) : -INFINITY); \
+  }
+      AT_MAX_GRANULE(0, v0) AT_MAX_GRANULE(1, v1) AT_MAX_GRANULE(2, v2) AT_MAX_GRANULE(3, v3)
+      AT_MAX_GRANULE(4, v4) AT_MAX_GRANULE(5, v5) AT_MAX_GRANULE(6, v6)
+      if constexpr (NG > 7) { AT_MAX_GRANULE(7, v7) }
+#undef AT_MAX_GRANULE
+      // p = exp2((s - max) * scale), row sum in fp32, bf16 pairs back into the slot's first columns (every S column is in registers)
       const float mscaled = fmaxf(mx0, mx1) * scale_log2e;
       float sum0 = 0.f, sum1 = 0.f;
-      load_batch(0);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        if (2 * b < n16) {
-          tmem_ld_wait();
-          if (2 * (b + 1) < n16) load_batch(b + 1);
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int g = 2 * b + hh;
-            if (g < n16) {
-              const uint32_t* v = buf[b & 1] + hh * 16;
-              uint32_t pk[8];
-              if (g < n16 - 1) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                  const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mscaled));
-                  const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mscaled));
-                  sum0 += p0;
-                  sum1 += p1;
-                  pk[j >> 1] = pack_bf16x2(p0, p1);
-                }
-              } else {  // the window's last granule: keys at or beyond `tail` get p = 0 (select, so NaN / Inf scores cannot leak)
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                  const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mscaled));
-                  const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mscaled));
-                  const float p0 = j < tail ? e0 : 0.f, p1 = j + 1 < tail ? e1 : 0.f;
-                  sum0 += p0;
-                  sum1 += p1;
-                  pk[j >> 1] = pack_bf16x2(p0, p1);
-                }
-              }
-              // P columns [8g, 8g+8), g <= 2b+1, end at 16b+16 <= 32(b+1): below every S column still to be read or in flight
-              tmem_st8(t_s + g * 8, pk);
-            }
-          }
-        }
-      }
+#define AT_EXP_GRANULE(G, V)                                                                        \
+  if ((G) < n16) {                                                                                 \
+    uint32_t pk[8];                                                                                \
+    const int live = (G) < n16 - 1 ? 16 : tail; /* keys at or beyond `live` get p = 0 by select: NaN / Inf scores cannot leak */ \
+    _Pragma("unroll") for (int j = 0; j < 16; j += 2) {                                            \
+      const float e0 = ex2_approx(fmaf(__uint_as_float(V[j]), scale_log2e, -mscaled));             \
+      const float e1 = ex2_approx(fmaf(__uint_as_float(V[j + 1]), scale_log2e, -mscaled));         \
+      const float p0 = j < live ? e0 : 0.f, p1 = j + 1 < live ? e1 : 0.f;                          \
+      sum0 += p0;                                                                                  \
+      sum1 += p1;                                                                                  \
+      pk[j >> 1] = pack_bf16x2(p0, p1);                                                            \
+    }                                                                                              \
+    tmem_st8(t_s + (G) * 8, pk);                                                                   \
+  }
+      AT_EXP_GRANULE(0, v0) AT_EXP_GRANULE(1, v1) AT_EXP_GRANULE(2, v2) AT_EXP_GRANULE(3, v3)
+      AT_EXP_GRANULE(4, v4) AT_EXP_GRANULE(5, v5) AT_EXP_GRANULE(6, v6)
+      if constexpr (NG > 7) { AT_EXP_GRANULE(7, v7) }
+#undef AT_EXP_GRANULE
       const float sum = sum0 + sum1;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[wg]);
+      if (lane == 0) mbar_arrive(&p_full[slot]);
 
       // O = P V is ready: normalise, round, store this row's 64 dims (128 contiguous bytes)
-      at_wait(&o_full[wg], ph);
+      at_wait(&o_full[slot], ph);
       tc_fence_after();
       const float inv = 1.0f / sum;
       __nv_bfloat16* orow = out + (static_cast<long long>(wd.x) + row) * d + h * AT_HD;
@@ -315,7 +295,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       // the slot may be overwritten by the next item's Q K^T as soon as every warp has its O row in registers
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[wg]);
+      if (lane == 0) mbar_arrive(&o_empty[slot]);
       if (row < wl) {
 #pragma unroll
         for (int g = 0; g < AT_HD / 8; ++g) reinterpret_cast<uint4*>(orow)[g] = packed[g];
