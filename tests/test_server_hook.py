@@ -167,3 +167,21 @@ def test_through_the_references_own_do_transcribe(monkeypatch):
     server._do_transcribe(audio, 16000, None, False)
     assert m.tower.calls == 1
     sys.modules.pop("server", None)
+
+
+def test_forced_aligner_reuses_the_same_slot(monkeypatch):
+    """the ForcedAligner (src/subtitle.py:315-331) is the same audio-tower family behind the same SDK layout
+    (.model.thinker.audio_tower), so the same loader / patch serves /v1/audio/subtitles: a third model gets its own backend and
+    only its own tower is patched while it runs."""
+    monkeypatch.setenv("B200_ENCODER", "1")
+    asr, aligner = FakeSDKModel(), FakeSDKModel()
+    aligner.align = lambda audio_sr, text, language=None: aligner.transcribe(audio_sr)     # Qwen3ForcedAligner.align runs the tower too
+    b_asr, b_al = FakeBackend(), FakeBackend()
+    made = iter([b_asr, b_al])
+    assert server_hook.try_load_b200_encoder(asr, factory=lambda t: next(made)) == 1
+    assert server_hook.try_load_b200_encoder(aligner, factory=lambda t: next(made)) == 1   # lazy load_aligner() calls it again
+    orig = aligner.tower.forward
+    server_hook.run_transcribe(aligner, lambda: aligner.align((np.zeros(10), 16000), "hello"))
+    assert (b_asr.calls, b_al.calls) == (0, 1)
+    assert aligner.tower.forward == orig and aligner.tower.calls == 0                      # restored; the torch forward never ran
+    assert float(aligner.seen[0][0, 0]) == 7.0
