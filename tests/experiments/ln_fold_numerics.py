@@ -1,5 +1,5 @@
 import sys, numpy as np, torch, torch.nn.functional as F
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import oracle
 from oracle import encoder as E
 from oracle.signals import speech_like
