@@ -576,3 +576,34 @@ def test_encode_into_equals_masked_scatter(tiny):
             small.encode_into(mel, flens, got, bad)
     finally:
         small.close()
+
+
+@pytest.mark.parametrize("mode", ["unfused", "stats_kernel", "epilogue_stats"])
+def test_layernorm_modes_agree(tiny, golden, mode):
+    """QASR_LN switches: the separate LayerNorm kernel, the folded LayerNorm with a statistics pass (default) and the folded
+    LayerNorm with statistics from the residual epilogues all meet the parity bar and agree with each other to bf16 noise."""
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import B200AudioEncoder
+
+    cfg, w, enc = tiny
+    os.environ["QASR_LN"] = mode
+    try:
+        other = B200AudioEncoder(cfg, w, max_chunks=64)
+    finally:
+        os.environ.pop("QASR_LN")
+    try:
+        lens = [int(t) for t in golden["enc_tiny_lens"]]
+        clips = [speech_like(t * 160, 50 + i) for i, t in enumerate(lens)]
+        a, _ = enc.encode_pcm(clips)
+        b, toks = other.encode_pcm(clips)
+        torch.cuda.synchronize()
+        a, b = a.float().cpu().numpy(), b.float().cpu().numpy()
+        s = 0
+        for i, n in enumerate(toks):
+            assert range_rel(b[s:s + int(n)], golden[f"enc_tiny_{i}"]) <= HID_TOL, (mode, i)
+            s += int(n)
+        assert range_rel(b, a) <= HID_TOL
+        if mode == "stats_kernel":
+            assert np.array_equal(a, b)          # the default mode
+    finally:
+        other.close()
