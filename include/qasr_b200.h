@@ -205,6 +205,9 @@ QASR_API size_t qasr_pool_workspace_bytes(qasr_pool_t p);
 QASR_API int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                               int64_t out_capacity_tokens, int64_t* token_lens_out, int32_t* clip_device_out, uint64_t* ticket_out);
 QASR_API int qasr_pool_collect(qasr_pool_t p, uint64_t ticket);
+/* The sharding rule of qasr_pool_submit on its own (pure host code, no GPU needed): clip_shard_out[i] = index (0 .. n_devices-1)
+ * of the pool member clip i would be sent to -- contiguous ranges of near-equal mel-frame count. */
+QASR_API int qasr_pool_plan(const int64_t* clip_offsets, int n_clips, int n_devices, int32_t* clip_shard_out);
 QASR_API void qasr_pool_destroy(qasr_pool_t p);
 
 /* ---- launch accounting and per-launch timing (measurement; bench.py's roofline figures) ------- */

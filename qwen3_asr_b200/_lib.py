@@ -62,6 +62,7 @@ SIGNATURES = {
     "qasr_pool_workspace_bytes": (C.c_size_t, [_P]),
     "qasr_pool_submit": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "qasr_pool_collect": (C.c_int, [_P, C.c_uint64]),
+    "qasr_pool_plan": (C.c_int, [_I64P, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "qasr_pool_destroy": (None, [_P]),
     "qasr_launch_count": (C.c_uint64, [_P]),
     "qasr_profile_enable": (C.c_int, [_P, C.c_int]),

@@ -65,6 +65,24 @@ struct qasr_pool_s {
 
 namespace {
 
+// Contiguous partition of the clips into g ranges of near-equal work (mel frames): cut after the clip at which the running total
+// crosses k / g of the work (k = 1 .. g - 1), rounding to the nearer side of the boundary clip.  With many clips per GPU this is
+// within one clip of the optimum; with fewer clips than GPUs some ranges are empty.  cut has g + 1 entries, cut[0] = 0, cut[g] = n.
+void partition_clips(const std::vector<int64_t>& frames, int g, std::vector<int>* cut) {
+  const int n = static_cast<int>(frames.size());
+  int64_t total = 0;
+  for (int64_t f : frames) total += f;
+  cut->assign(g + 1, n);
+  (*cut)[0] = 0;
+  int i = 0;
+  int64_t run = 0;
+  for (int k = 1; k < g; ++k) {
+    const double target = static_cast<double>(total) * k / g;
+    while (i < n && static_cast<double>(run) + 0.5 * static_cast<double>(frames[i]) <= target) run += frames[i++];
+    (*cut)[k] = std::max(i, (*cut)[k - 1]);
+  }
+}
+
 void finish_shard(qasr_pool_s* p, Shard& s, int rc) {
   std::string err;
   if (rc != 0) {
@@ -184,31 +202,17 @@ int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_o
   QASR_REQUIRE(pcm_host != nullptr && out_host != nullptr, "qasr_pool_submit: null buffer");
   // work per clip = mel frames; token counts give every shard its slice of the output (clip order)
   std::vector<int64_t> frames(n_clips), tok_off(n_clips + 1, 0);
-  int64_t total_frames = 0;
   for (int i = 0; i < n_clips; ++i) {
     const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
     QASR_REQUIRE(n >= 0, "qasr_pool_submit: offsets must be non-decreasing");
     frames[i] = n / 160;
-    total_frames += frames[i];
     token_lens_out[i] = qasr_token_len(frames[i]);
     tok_off[i + 1] = tok_off[i] + token_lens_out[i];
   }
   QASR_REQUIRE(tok_off[n_clips] <= out_capacity_tokens, "qasr_pool_submit: output buffer too small for " + std::to_string(tok_off[n_clips]) + " tokens");
-  // contiguous partition: cut after the clip at which the running total crosses k / G of the work (k = 1 .. G - 1), rounding to
-  // the nearer side of the boundary clip.  With many clips per GPU this is within one clip of the optimum; with fewer clips than
-  // GPUs some workers get nothing.
   const int g = static_cast<int>(p->workers.size());
-  std::vector<int> cut(g + 1, n_clips);
-  cut[0] = 0;
-  {
-    int i = 0;
-    int64_t run = 0;
-    for (int k = 1; k < g; ++k) {
-      const double target = static_cast<double>(total_frames) * k / g;
-      while (i < n_clips && static_cast<double>(run) + 0.5 * static_cast<double>(frames[i]) <= target) run += frames[i++];
-      cut[k] = std::max(i, cut[k - 1]);
-    }
-  }
+  std::vector<int> cut;
+  partition_clips(frames, g, &cut);
   auto batch = std::make_shared<Batch>();
   std::vector<std::pair<int, Shard>> shards;
   for (int k = 0; k < g; ++k) {
@@ -233,6 +237,20 @@ int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_o
     *ticket_out = t;
   }
   p->cv_work.notify_all();
+  return 0;
+}
+
+int qasr_pool_plan(const int64_t* clip_offsets, int n_clips, int n_devices, int32_t* clip_shard_out) {
+  QASR_REQUIRE(clip_offsets != nullptr && clip_shard_out != nullptr && n_clips >= 0 && n_devices >= 1, "qasr_pool_plan: bad argument");
+  std::vector<int64_t> frames(n_clips);
+  for (int i = 0; i < n_clips; ++i) {
+    QASR_REQUIRE(clip_offsets[i + 1] >= clip_offsets[i], "qasr_pool_plan: offsets must be non-decreasing");
+    frames[i] = (clip_offsets[i + 1] - clip_offsets[i]) / 160;
+  }
+  std::vector<int> cut;
+  partition_clips(frames, n_devices, &cut);
+  for (int k = 0; k < n_devices; ++k)
+    for (int i = cut[k]; i < cut[k + 1]; ++i) clip_shard_out[i] = k;
   return 0;
 }
 

@@ -145,3 +145,39 @@ def test_fast_gelu_formula_over_all_bf16_inputs():
     mism = (torch.from_numpy(got).to(torch.bfloat16) != ref_bf).sum().item()
     torch_mism = (torch.nn.functional.gelu(xt).to(torch.bfloat16) != ref_bf).sum().item()
     assert mism <= 2 * max(torch_mism, 100), (mism, torch_mism)
+
+
+def test_pool_sharding_rule_on_the_host(lib):
+    """qasr_pool_plan = the rule qasr_pool_submit shards by: contiguous clip ranges, near-equal mel-frame counts, every clip placed,
+    empty ranges only when there are fewer clips than devices.  Pure host code: runs without a GPU."""
+    import ctypes as C
+
+    rng = np.random.default_rng(1234)
+
+    def plan(lens, g):
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out = np.full(len(lens), -1, dtype=np.int32)
+        rc = lib.qasr_pool_plan(offs.ctypes.data_as(C.POINTER(C.c_int64)), len(lens), g, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        assert rc == 0
+        return out
+
+    # BASELINE config 4: one hour of 1-30 s segments over 2 / 4 / 8 GPUs
+    lens, total = [], 0
+    while total < 3600 * 16000:
+        ln = min(int(round(rng.uniform(1.0, 30.0) / 0.01)) * 160, 3600 * 16000 - total)
+        lens.append(ln)
+        total += ln
+    frames = np.array(lens) // 160
+    for g in (1, 2, 4, 8):
+        s = plan(lens, g)
+        assert s.min() == 0 and s.max() == g - 1 and np.all(np.diff(s) >= 0)            # contiguous, every device used
+        load = np.array([frames[s == k].sum() for k in range(g)])
+        assert load.max() <= frames.sum() / g + frames.max()                            # within one clip of the ideal share
+        assert load.max() / (frames.sum() / g) - 1.0 <= 0.05                            # C4: < 5 % imbalance even at 8 GPUs
+    # fewer clips than devices, equal clips, a zero-length clip, nothing at all
+    assert plan([16000, 16000], 4).tolist() == [0, 2]                                  # one clip each on two of the four devices
+    s = plan([16000] * 8, 4)
+    assert s.tolist() == [0, 0, 1, 1, 2, 2, 3, 3]
+    s = plan([16000, 0, 16000, 16000], 2)
+    assert np.all(np.diff(s) >= 0) and set(s.tolist()) == {0, 1}
+    assert plan([], 3).tolist() == []
