@@ -507,6 +507,16 @@ def test_full_size_properties_1p7b():
         assert err <= HID_TOL, err
     finally:
         enc.close()
+    # one micro-batch of 180 chunks (>= the SM count: the large-CTA conv1 configuration, ~16 GEMM row-block pairs) against a lone
+    # clip (small-CTA conv1, a single row-block pair): the grid shapes differ, every output bit must not
+    big = B200AudioEncoder(cfg, w)
+    try:
+        c, _ = big.encode_pcm(clips)
+        assert torch.equal(c, a)
+        lone, _ = big.encode_pcm(clips[2:3])
+        assert torch.equal(lone, c[2 * 390:3 * 390])
+    finally:
+        big.close()
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
