@@ -586,41 +586,6 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __re
 }
 }  // namespace
 
-namespace {
-// (sum, sum of squares) per row and 32-column panel, left by the residual epilogues (epilogues.cuh RowStats) -> (mean, rstd).
-// Fixed summation order: deterministic.  var = E[x^2] - mean^2 in fp32 (clamped at 0).
-__global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __restrict__ part, int n_panels, float2* __restrict__ stats,
-                                                                int rows, float inv_d, float eps) {
-  // one warp per row, one panel per lane (d <= 2048: at most two rounds): a coalesced 256-byte read, then a butterfly whose
-  // summation order is fixed by the lane ids
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float2* p = part + static_cast<long long>(row) * n_panels;
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = lane; i < n_panels; i += 32) {
-    const float2 v = __ldg(p + i);
-    s1 += v.x;
-    s2 += v.y;
-  }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if (lane == 0) {
-    const float mean = s1 * inv_d;
-    const float var = fmaxf(fmaf(-mean, mean, s2 * inv_d), 0.f);
-    stats[row] = make_float2(mean, rsqrtf(var + eps));
-  }
-}
-}  // namespace
-
-cudaError_t launch_ln_stats_finalize(const float2* part, int n_panels, float2* stats, int rows, int d, float eps, cudaStream_t stream) {
-  if (rows == 0) return cudaSuccess;
-  if (n_panels * 32 != d) return cudaErrorInvalidValue;
-  return launch_pdl(ln_stats_finalize_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, 1, part, n_panels, stats, rows, 1.0f / d, eps);
-}
-
 cudaError_t launch_ln_stats(const __nv_bfloat16* x, float2* stats, int rows, int d, float eps, cudaStream_t stream) {
   if (rows == 0) return cudaSuccess;
   if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;

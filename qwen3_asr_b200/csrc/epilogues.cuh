@@ -241,7 +241,7 @@ struct EpiConvOut {
 
 // The epilogues that write the residual stream (conv_out, out_proj, fc2) can also leave what the NEXT LayerNorm needs: per row and
 // 32-column panel the sum and the sum of squares of the bf16 values just stored, in fixed slots part[row][panel] (deterministic:
-// no atomics).  ln_stats_finalize_kernel turns the d / 32 partials of a row into (mean, rstd) for the LnFold<> consumer.
+// no atomics).  The consuming GEMM (LnFoldPart<>) turns the d / 32 partials of a row into (mean, rstd) in its idle warps.
 template <class Base>
 struct RowStats : Base {
   float2* part;      // [rows][n_panels]

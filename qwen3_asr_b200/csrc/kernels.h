@@ -67,8 +67,6 @@ cudaError_t launch_layernorm(const __nv_bfloat16* x, const float* gamma, const f
 
 // (mean, rstd) per row only: for the Linears that have the LayerNorm folded in (epilogues.cuh LnFold)
 cudaError_t launch_ln_stats(const __nv_bfloat16* x, float2* stats, int rows, int d, float eps, cudaStream_t stream);
-// ... or from the per-panel partial sums the residual epilogues left (epilogues.cuh RowStats): part [rows][n_panels = d / 32]
-cudaError_t launch_ln_stats_finalize(const float2* part, int n_panels, float2* stats, int rows, int d, float eps, cudaStream_t stream);
 
 // LayerNorm whose bf16-rounded output row is quantised to e4m3 with a per-row dynamic scale in the same pass (fp8 per-row mode)
 cudaError_t launch_layernorm_fp8(const __nv_bfloat16* x, const float* gamma, const float* beta, uint8_t* q_out, float* row_scale,
