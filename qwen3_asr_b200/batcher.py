@@ -22,11 +22,15 @@ from typing import Callable, Sequence
 
 class WindowBatcher:
     def __init__(self, encode: Callable[[Sequence, Sequence[bool]], tuple], max_wait_ms: float = 5.0, max_audio_s: float = 1024.0,
-                 seconds_of: Callable[[object], float] | None = None):
-        """encode(windows, flush_flags) -> (hidden [sum tokens, D], token_lens [n]) for the whole batch, clip-major."""
+                 seconds_of: Callable[[object], float] | None = None, empty: Callable[[], object] | None = None):
+        """encode(windows, flush_flags) -> (hidden [sum tokens, D], token_lens [n]) for the whole batch, clip-major.
+        Empty windows (the reference returns '' for them before any inference, src/server.py:1331-1332) never reach ``encode``:
+        their future resolves to ``hidden[:0]`` of the batch they arrived with (or ``empty()`` when the whole batch was empty),
+        so one client's empty flush cannot fail the windows of other clients."""
         self._encode = encode
         self.max_wait = max_wait_ms / 1000.0
         self.max_audio_s = float(max_audio_s)
+        self._empty = empty or (lambda: None)
         self._seconds_of = seconds_of or (lambda w: len(w) / (2 * 16000.0) if isinstance(w, (bytes, bytearray)) else len(w) / 16000.0)
         self._lock = threading.Condition()
         self._pending = []          # (window, flush, future, t_arrival)
@@ -86,13 +90,17 @@ class WindowBatcher:
             futs = [b[2] for b in batch]
             live = [f.set_running_or_notify_cancel() for f in futs]
             try:
-                hidden, token_lens = self._encode([b[0] for b in batch], [b[1] for b in batch])
+                keep = [i for i, b in enumerate(batch) if self._seconds_of(b[0]) > 0]
+                hidden, token_lens = None, []
+                if keep:
+                    hidden, token_lens = self._encode([batch[i][0] for i in keep], [batch[i][1] for i in keep])
                 self.batches.append(len(batch))
+                lens = dict(zip(keep, token_lens))
                 start = 0
-                for f, ok, n in zip(futs, live, token_lens):
-                    n = int(n)
+                for i, (f, ok) in enumerate(zip(futs, live)):
+                    n = int(lens.get(i, 0))
                     if ok:
-                        f.set_result(hidden[start:start + n])
+                        f.set_result(hidden[start:start + n] if hidden is not None else self._empty())
                     start += n
             except BaseException as e:  # the whole batch shares the failure, as a failing job does in the reference (server.py:93-94)
                 for f, ok in zip(futs, live):

@@ -11,6 +11,9 @@
 //   warp 1        MMA issuer: S = Q K^T (kind::f16, M = 128, N = keys rounded to 16, K = 64) into TMEM;
 //                 O = P V with P read from TMEM (A operand) and V used as an MN-major B operand straight from its
 //                 row-major tile -- no transposes, no smem round trip for S or P
+//   warp 3        clip isolation: P V runs over keys rounded up to 16, and the V tile's rows past the window's end belong to the
+//                 next window (another clip) or are stale; a NaN / Inf there would turn 0 * x into NaN.  This warp overwrites
+//                 those (<= 15) rows of the landed V tile with zeros before P V may read it (v_ready barrier)
 //   warp 2        TMEM allocation: 4 slots x 128 columns.  A slot holds S (<= 128 fp32 columns); P (bf16 pairs) overwrites its
 //                 first 64 columns as the softmax proceeds, and O (64 fp32 columns) is accumulated into columns 64..127 --
 //                 the upper half of S, dead once the whole row has been read -- so four items fit where two did
@@ -44,7 +47,7 @@ struct AtCfg {
   static constexpr int TILE_BYTES = TR * AT_HD * 2;
   static constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // Q, K, V
   static constexpr int STAGES = TR <= 112 ? 5 : 4;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 512;
   static_assert(STAGE_BYTES % 1024 == 0, "stages keep the 1024-byte alignment of SWIZZLE_128B tiles");
   static_assert(SMEM <= 232448, "exceeds the shared memory a CTA can opt in to");
 };
@@ -96,7 +99,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
   uint64_t* p_full = s_full + AT_SLOTS;         // [SLOTS] softmax -> MMA: P is in TMEM
   uint64_t* o_full = s_full + 2 * AT_SLOTS;     // [SLOTS] MMA -> softmax: O is in TMEM
   uint64_t* o_empty = s_full + 3 * AT_SLOTS;    // [SLOTS] softmax -> MMA: the slot is drained (O aliases S: the next QK^T waits for it)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 4 * AT_SLOTS);
+  uint64_t* v_ready = s_full + 4 * AT_SLOTS;    // [STAGES] warp 3 -> MMA: V rows past the window's end are zero
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(v_ready + AT_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_win * heads;
@@ -106,6 +110,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
     for (int i = 0; i < AT_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&v_ready[i], 1);
     }
     for (int i = 0; i < AT_SLOTS; ++i) {
       mbar_init(&s_full[i], 1);
@@ -174,6 +179,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       const int wl = __ldg(&win[item / heads]).y;
       const int n16 = (wl + 15) >> 4;
       at_wait(&p_full[t], pht);
+      at_wait(&v_ready[s], (it / AT_STAGES) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dv = desc0 + static_cast<uint64_t>((s * AT_STAGE_BYTES + 2 * AT_TILE_BYTES) >> 4);
@@ -195,6 +201,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int2* __re
       if (it >= AT_LOOKAHEAD) issue_pv(it - AT_LOOKAHEAD, item - AT_LOOKAHEAD * step);
     }
     for (int j = it >= AT_LOOKAHEAD ? it - AT_LOOKAHEAD : 0; j < it; ++j) issue_pv(j, static_cast<int>(blockIdx.x) + j * step);
+  } else if (warp == 3) {
+    // ===================== V tail rows -> zero (clip isolation) =====================
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it % AT_STAGES;
+      const uint32_t ph = (it / AT_STAGES) & 1;
+      const int wl = __ldg(&win[item / heads]).y;
+      const int r1 = ((wl + 15) >> 4) << 4;
+      at_wait(&full_bar[s], ph);
+      if (r1 > wl) {
+        // SWIZZLE_128B permutes 16-byte chunks inside a 128-byte row: row r is bytes [128 r, 128 r + 128) of the tile
+        const uint32_t v0 = smem_u32(smem + s * AT_STAGE_BYTES + 2 * AT_TILE_BYTES) + static_cast<uint32_t>(wl) * 128u;
+        for (int i = lane; i < (r1 - wl) * 8; i += 32) st_shared_v4(v0 + static_cast<uint32_t>(i) * 16u, make_uint4(0u, 0u, 0u, 0u));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&v_ready[s]);
+    }
   } else if (warp >= 4) {
     // ===================== softmax + output warpgroups =====================
     const int wg = (warp - 4) >> 2;            // 0 .. AT_WGS-1: this warpgroup serves items it % AT_WGS == wg (slot it % AT_SLOTS)

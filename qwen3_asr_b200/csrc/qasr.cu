@@ -8,6 +8,8 @@
 
 #include <cuda_fp16.h>
 
+#include <initializer_list>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -31,6 +33,22 @@ bool pdl_enabled() {
     return !(e != nullptr && e[0] == '0');
   }();
   return on;
+}
+// Value of a QASR_* switch: index into `allowed` (0 when the variable is unset or empty), -1 for anything else -- a mistyped
+// switch is an error (qasr_create fails), never a silent default.
+int env_choice(const char* name, std::initializer_list<const char*> allowed) {
+  const char* e = std::getenv(name);
+  if (e == nullptr || e[0] == '\0') return 0;
+  int i = 0;
+  std::string list;
+  for (const char* a : allowed) {
+    if (std::strcmp(e, a) == 0) return i;
+    list += (i != 0 ? ", " : "");
+    list += a;
+    ++i;
+  }
+  set_last_error(std::string(name) + "=" + e + " is not a known value (expected one of: " + list + ")");
+  return -1;
 }
 }  // namespace qasr
 
@@ -114,6 +132,7 @@ struct qasr_handle_s {
   bool ln_epi_stats = false;   // row statistics come from the producing GEMM's epilogue instead of a pass over x
   CUtensorMap tm_x;
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
+  bool use_graph = true;    // QASR_GRAPH=0: launch every kernel eagerly even for small batches (A/B, debugging)
   int chunks_per_window = 8;
   int attn_tile_rows = 128;  // token rows of the attention kernel's TMA tiles (112 when every window fits)
   int max_chunks = 0, max_tokens = 0;
@@ -155,7 +174,14 @@ struct qasr_handle_s {
     GrowBuf pcm, out;
     cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
     uint64_t seq = 0;  // ticket of the submit that last used this slot (0 = never)
+    bool waited = true;  // qasr_wait has been called for `seq`
   } pipe[2];
+  // The workspaces (act1..3, x, qkv, att, ffn, mel_buf, ...) are ordered by the caller's stream only.  When a call arrives on a
+  // different stream than the previous one (the hook reads torch.cuda.current_stream(): server._cuda_stream vs the default
+  // stream on the aligner / WS paths), the new stream first waits for the previous call's work.
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   uint64_t next_ticket = 1;
 
@@ -222,6 +248,18 @@ int staging_acquire(qasr_handle_s* h, size_t bytes, Staging** out) {
     h->device_bytes += want;
   }
   *out = s;
+  return 0;
+}
+
+int stream_enter(qasr_handle_s* h, cudaStream_t stream) {
+  if (h->ev_last == nullptr) QASR_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
+  if (h->has_last && stream != h->last_stream) QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, h->ev_last, 0));
+  return 0;
+}
+int stream_leave(qasr_handle_s* h, cudaStream_t stream) {
+  QASR_CUDA_CHECK(cudaEventRecord(h->ev_last, stream));
+  h->last_stream = stream;
+  h->has_last = true;
   return 0;
 }
 
@@ -580,23 +618,31 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->max_tokens = cfg->max_tokens > 0 ? cfg->max_tokens : h->max_chunks * kTokPerChunk;
   h->max_chunks = std::max(h->max_chunks, h->chunks_per_window);
   h->max_tokens = std::max(h->max_tokens, h->chunks_per_window * kTokPerChunk);
-  const char* e = std::getenv("QASR_DEBUG_SIMT");
-  h->simt = e != nullptr && e[0] == '1';
+  // experiment / checker switches: unknown values are an error, not a silent default
+  const int v_simt = env_choice("QASR_DEBUG_SIMT", {"0", "1"});
+  const int v_ln = env_choice("QASR_LN", {"fold", "unfused", "epilogue_stats"});
+  const int v_att = env_choice("QASR_ATTENTION", {"tc", "mma_sync"});
+  const int v_keep = env_choice("QASR_DEBUG_KEEP", {"0", "1"});
+  const int v_pdl = env_choice("QASR_PDL", {"1", "0"});
+  const int v_graph = env_choice("QASR_GRAPH", {"1", "0"});
+  if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0) {
+    delete h;
+    return 1;
+  }
+  h->simt = v_simt == 1;
   if (h->simt && h->fp8) {
     set_last_error("QASR_DEBUG_SIMT=1 is not available in fp8 mode (the SIMT checker reads bf16 operands)");
     delete h;
     return 1;
   }
-  e = std::getenv("QASR_LN");
-  h->ln_fold = !h->fp8 && !h->simt && !(e != nullptr && std::string(e) == "unfused");
+  h->ln_fold = !h->fp8 && !h->simt && v_ln != 1;
   // QASR_LN=epilogue_stats: the residual epilogues leave per-panel partial sums (RowStats<>) and the consuming GEMM's idle warps
   // finalise them per tile (LnFoldPart<>): no statistics kernel at all.  Parity-green but measured no faster (12.1 vs 12.0 ms per
   // step: what the removed pass saves, the epilogues pay) -- kept as an experiment switch, off by default.
-  h->ln_epi_stats = h->ln_fold && cfg->d_model % 64 == 0 && e != nullptr && std::string(e) == "epilogue_stats";
-  e = std::getenv("QASR_ATTENTION");
-  h->attn_simt = e != nullptr && std::string(e) == "mma_sync";
-  e = std::getenv("QASR_DEBUG_KEEP");
-  h->keep_debug = e != nullptr && e[0] == '1';
+  h->ln_epi_stats = h->ln_fold && cfg->d_model % 64 == 0 && v_ln == 2;
+  h->attn_simt = v_att == 1;
+  h->keep_debug = v_keep == 1;
+  h->use_graph = v_graph == 0;
 
   mel::Tables* host_tables = new mel::Tables();
   int rc = 0;
@@ -809,8 +855,10 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   size_t n_items = 0;
   for (int i = 0; i < n_clips; ++i) {
     const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
-    QASR_REQUIRE(n > mel::N_FFT / 2, "qasr_logmel: every clip needs more than 200 samples (reflect padding), clip " + std::to_string(i) +
-                                        " has " + std::to_string(n));
+    // an empty clip is valid (an empty WS window: 0 frames, 0 tokens, server.py:1331 returns '' for it); 1..200 samples cannot be
+    // reflect-padded (torch.stft raises for them too)
+    QASR_REQUIRE(n == 0 || n > mel::N_FFT / 2, "qasr_logmel: a non-empty clip needs more than 200 samples (reflect padding), clip " +
+                                                   std::to_string(i) + " has " + std::to_string(n));
     QASR_REQUIRE(n < (1LL << 31), "qasr_logmel: clip too long");
     const int64_t t = n / mel::HOP;
     if (feature_lens_out != nullptr) feature_lens_out[i] = t;
@@ -819,6 +867,7 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   }
   QASR_REQUIRE(mel_ld >= cols, "qasr_logmel: mel_ld smaller than the total frame count");
   if (cols == 0) return 0;
+  if (stream_enter(h, stream) != 0) return 2;
 
   // Work list in ticket order: frame items clip by clip; the clamp items of a clip are emitted once kClampLag frame
   // items of later clips lie behind it (or at the end), so that a clamp practically never waits.  Every frame item a
@@ -872,7 +921,7 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   st->in_flight = true;
   h->last_mel_cols = cols;
   h->last_mel_ld = mel_ld;
-  return 0;
+  return stream_leave(h, stream);
 }
 
 namespace {
@@ -932,6 +981,7 @@ int encode_impl(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel
   QASR_REQUIRE(mel_ld >= col, "qasr_encode: mel_ld smaller than the total frame count");
   if (total_tokens == 0) return 0;
   QASR_REQUIRE(mel_dev != nullptr && out_dev != nullptr, "qasr_encode: null buffer");
+  if (stream_enter(h, stream) != 0) return 2;
 
   size_t ui = 0;
   long long tok_off = 0;
@@ -977,7 +1027,7 @@ int encode_impl(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel
   }
   h->last_mel_cols = col;
   h->last_mel_ld = mel_ld;
-  return 0;
+  return stream_leave(h, stream);
 }
 }  // namespace
 
@@ -1024,6 +1074,8 @@ int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* 
       QASR_CUDA_CHECK(cudaEventCreateWithFlags(&pp.ev_out, cudaEventDisableTiming));
     }
   }
+  QASR_REQUIRE(h->pipe[h->next_ticket & 1].waited, "qasr_submit_pcm_host: two submits are already un-waited; call qasr_wait on ticket " +
+                                                      std::to_string(h->pipe[h->next_ticket & 1].seq) + " first");
   const uint64_t ticket = h->next_ticket++;
   qasr_handle_s::Pipe& pp = h->pipe[ticket & 1];
   const size_t out_bytes = static_cast<size_t>(tokens) * h->cfg.output_dim * sizeof(bf16);
@@ -1045,6 +1097,7 @@ int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* 
   if (out_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(out_host, pp.out.p, out_bytes, cudaMemcpyDeviceToHost, h->s_out));
   QASR_CUDA_CHECK(cudaEventRecord(pp.ev_out, h->s_out));
   pp.seq = ticket;
+  pp.waited = false;
   *ticket_out = ticket;
   return 0;
 }
@@ -1057,6 +1110,7 @@ int qasr_wait(qasr_handle_t h, uint64_t ticket) {
   qasr_handle_s::Pipe& pp = h->pipe[ticket & 1];
   // a later submit on the same slot waited for this ticket's copies on the device; its own event then covers both
   if (pp.seq != 0) QASR_CUDA_CHECK(cudaEventSynchronize(pp.ev_out));
+  if (pp.seq == ticket) pp.waited = true;
   return 0;
 }
 
@@ -1111,6 +1165,7 @@ int qasr_resample_pcm16(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t
   const size_t desc_bytes = align_up(sizeof(RsStream) * static_cast<size_t>(n_streams), 16);
   const size_t total = desc_bytes + sizeof(double) * static_cast<size_t>(n_taps);
   Staging* st = nullptr;
+  if (stream_enter(h, stream) != 0) return 2;
   if (staging_acquire(h, total, &st) != 0) return 2;
   RsStream* d = reinterpret_cast<RsStream*>(st->host);
   for (int i = 0; i < n_streams; ++i)
@@ -1123,7 +1178,7 @@ int qasr_resample_pcm16(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t
                                     h->num_sms, stream));
   QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
   st->in_flight = true;
-  return 0;
+  return stream_leave(h, stream);
 }
 
 int qasr_ws_window(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_offsets, int n_streams, const int32_t* pad_samples,
@@ -1159,6 +1214,7 @@ int qasr_ws_window(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_
   QASR_REQUIRE(pcm16_dev != nullptr && out_dev != nullptr, "qasr_ws_window: null buffer");
   const size_t total = sizeof(WsStream) * static_cast<size_t>(n_streams);
   Staging* st = nullptr;
+  if (stream_enter(h, stream) != 0) return 2;
   if (staging_acquire(h, total, &st) != 0) return 2;
   WsStream* d = reinterpret_cast<WsStream*>(st->host);
   for (int i = 0; i < n_streams; ++i) {
@@ -1170,7 +1226,7 @@ int qasr_ws_window(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_
               stream, launch_ws_window(pcm16_dev, reinterpret_cast<const WsStream*>(st->dev), n_streams, max_out, sos, n_sections, warm, out_dev, stream));
   QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
   st->in_flight = true;
-  return 0;
+  return stream_leave(h, stream);
 }
 
 int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
@@ -1215,6 +1271,7 @@ void qasr_destroy(qasr_handle_t h) {
   for (auto& pp : h->pipe)
     for (cudaEvent_t e : {pp.ev_in, pp.ev_comp, pp.ev_out})
       if (e != nullptr) cudaEventDestroy(e);
+  if (h->ev_last != nullptr) cudaEventDestroy(h->ev_last);
   if (h->s_in != nullptr) cudaStreamDestroy(h->s_in);
   if (h->s_out != nullptr) cudaStreamDestroy(h->s_out);
   delete h;

@@ -18,6 +18,13 @@ an object with ``.last_hidden_state``.  Both shapes are supported.
 Env vars (same convention as TRT_ENCODER_PATH / ONNX_ENCODER_PATH: unset => behaviour unchanged):
     B200_ENCODER=1              enable the slot
     B200_ENCODER_LIB=/path.so   optional: library path (default: the in-tree libqasr_b200.so)
+    B200_FRONTEND=1             also replace the SDK processor's CPU WhisperFeatureExtractor by the CUDA log-mel kernel
+    B200_BATCH_WINDOWS=1        also encode concurrently queued windows as one ragged batch (queue_binding.py)
+
+Lifetime: the reference unloads the model after IDLE_TIMEOUT (``_unload_model_sync`` server.py:478-496, ``unload_aligner``
+subtitle.py:334-341) and loads a NEW module object on the next request.  ``install()`` wraps both unload functions so the
+backends (weights + workspace, ~6 GB for 1.7B) are freed with the model, and the registry holds the tower by weak reference:
+a tower that was garbage-collected closes its backend, and a recycled ``id()`` can never resolve to a stale backend.
 """
 
 from __future__ import annotations
@@ -25,16 +32,65 @@ from __future__ import annotations
 import contextlib
 import logging
 import os
+import threading
+import weakref
 
 _log = logging.getLogger("qwen3_asr_b200")
 
+
+class _Entry:
+    """One backend bound to one live torch module (held weakly; modules that cannot be weakly referenced are held strongly)."""
+
+    def __init__(self, tower, backend):
+        self.backend = backend
+        try:
+            self._ref = weakref.ref(tower)
+            self._strong = None
+            # the tower was freed without an explicit unload(): release the backend's device memory with it
+            self._fin = weakref.finalize(tower, _close_backend, backend)
+        except TypeError:
+            self._ref, self._strong, self._fin = None, tower, None
+
+    def tower(self):
+        return self._strong if self._ref is None else self._ref()
+
+    def close(self):
+        if self._fin is not None:
+            self._fin.detach()
+        _close_backend(self.backend)
+
+
+def _close_backend(backend) -> None:
+    close = getattr(backend, "close", None)
+    if close:
+        close()
+
+
 # one backend per torch module (dual-model mode keeps a 1.7B and a 0.6B tower resident, server.py:411-425)
-_b200_encoders: dict[int, object] = {}
+_b200_encoders: list[_Entry] = []
 _fallback_logged = False
+# per-thread context of the job the infer thread is running: a pre-computed encoder result for it (queue_binding.py)
+_job_ctx = threading.local()
+
+
+def _flag(name: str) -> bool:
+    return os.getenv(name, "") not in ("", "0", "false", "False")
 
 
 def enabled() -> bool:
-    return os.getenv("B200_ENCODER", "") not in ("", "0", "false", "False")
+    return _flag("B200_ENCODER")
+
+
+def _lookup(tower):
+    """The live entry bound to exactly this module object (dead entries are dropped on the way)."""
+    found = None
+    for e in list(_b200_encoders):
+        t = e.tower()
+        if t is None:
+            _b200_encoders.remove(e)   # its finalizer has already closed the backend
+        elif t is tower:
+            found = e
+    return found
 
 
 def find_audio_tower(m):
@@ -75,9 +131,9 @@ def try_load_b200_encoder(*models, log=None, factory=None) -> int:
             if tower is None:
                 log.error("B200 encoder: no audio tower found on the model object")
                 continue
-            if id(tower) in _b200_encoders:
+            if _lookup(tower) is not None:
                 continue
-            _b200_encoders[id(tower)] = (factory or _make_backend)(tower)
+            _b200_encoders.append(_Entry(tower, (factory or _make_backend)(tower)))
             log.info("B200 encoder backend ready")
             n += 1
         except Exception as e:  # same policy as the TRT / ONNX loaders: report and continue without it
@@ -85,20 +141,29 @@ def try_load_b200_encoder(*models, log=None, factory=None) -> int:
     return n
 
 
-def unload() -> None:
-    """Free the backends (call from ``_unload_model_sync``, server.py:478-496)."""
-    for enc in _b200_encoders.values():
-        close = getattr(enc, "close", None)
-        if close:
-            close()
-    _b200_encoders.clear()
+def unload(*models) -> None:
+    """Free the backends: all of them (``_unload_model_sync``, server.py:478-496), or only those of the given model objects
+    (``unload_aligner``, subtitle.py:334-341)."""
+    if not models:
+        doomed = list(_b200_encoders)
+    else:
+        towers = [find_audio_tower(m) for m in models if m is not None]
+        doomed = [e for e in _b200_encoders if any(e.tower() is t for t in towers if t is not None)]
+    for e in doomed:
+        e.close()
+        _b200_encoders.remove(e)
 
 
 def backend_for(m):
     tower = find_audio_tower(m)
     if tower is None:
         return None, None
-    return tower, _b200_encoders.get(id(tower))
+    e = _lookup(tower)
+    return tower, (e.backend if e is not None else None)
+
+
+def n_backends() -> int:
+    return sum(1 for e in _b200_encoders if e.tower() is not None)
 
 
 @contextlib.contextmanager
@@ -121,7 +186,10 @@ def patched_encoder(m, log=None):
             return _orig_fwd(*args, **kwargs)
         try:
             feature_lens = kwargs.get("feature_lens", args[1] if len(args) > 1 else None)
-            out = enc.forward(inp, feature_lens=feature_lens)
+            pre = getattr(_job_ctx, "prefetch", None)
+            out = pre.take(enc, inp, feature_lens) if pre is not None else None   # encoded ahead, batched with its queue neighbours
+            if out is None:
+                out = enc.forward(inp, feature_lens=feature_lens)
             return (out.last_hidden_state,) if legacy else out
         except Exception as e:  # TRT-slot convention: fall back to the original forward for this call
             if not _fallback_logged:
@@ -150,17 +218,52 @@ def run_transcribe(m, run, cuda_stream=None, log=None):
     return results
 
 
-def install(server_module, log=None) -> None:
-    """Zero-edit integration: wrap ``server._do_transcribe`` and ``server._load_model_sync`` in place.
+def install_frontend(m, log=None) -> bool:
+    """Replace ``m.processor.feature_extractor`` (the SDK processor's CPU WhisperFeatureExtractor, called at
+    vllm/transformers_utils/processors/qwen3_asr.py:114-130) by the CUDA log-mel kernel of this model's backend, so the mel
+    kernel is on the request path (SURVEY.md 8b "optional fused frontend entry").  Idempotent; False if there is nothing to patch."""
+    from .frontend import B200FeatureExtractor
 
-    After ``install(server)``, loading the model also runs ``try_load_b200_encoder(model, _fast_model)`` and every
-    ``_do_transcribe`` call runs with the selected model's audio tower patched.  With B200_ENCODER unset both
-    wrappers are pass-throughs."""
+    _, enc = backend_for(m)
+    proc = getattr(m, "processor", None)
+    if enc is None or proc is None or not hasattr(proc, "feature_extractor"):
+        return False
+    fe = proc.feature_extractor
+    if isinstance(fe, B200FeatureExtractor):
+        return True
+    proc.feature_extractor = B200FeatureExtractor(enc, original=fe)
+    (log or _log).info("B200 log-mel frontend installed")
+    return True
+
+
+def uninstall_frontend(m) -> None:
+    from .frontend import B200FeatureExtractor
+
+    proc = getattr(m, "processor", None)
+    fe = getattr(proc, "feature_extractor", None)
+    if isinstance(fe, B200FeatureExtractor) and fe.original is not None:
+        proc.feature_extractor = fe.original
+
+
+def install(server_module, log=None, frontend: bool | None = None, batch_windows: bool | None = None, subtitle_module=None) -> None:
+    """Zero-edit integration: wrap the reference's module-level functions in place.
+
+    After ``install(server)``:
+      * ``_load_model_sync`` also runs ``try_load_b200_encoder(model, _fast_model)`` (and, with ``frontend`` / B200_FRONTEND=1,
+        swaps the processors' feature extractor for the CUDA log-mel);
+      * ``_unload_model_sync`` (and ``subtitle.unload_aligner``) also free the backends, so the idle unload releases the VRAM;
+      * every ``_do_transcribe`` runs with the selected model's audio tower patched;
+      * with ``batch_windows`` / B200_BATCH_WINDOWS=1, ``_infer_queue.submit`` encodes the window of every queued job ahead of
+        time, batched with whatever else is queued (queue_binding.QueueBinding) -- PriorityInferQueue itself is untouched.
+    With B200_ENCODER unset every wrapper is a pass-through."""
     log = log or getattr(server_module, "log", None) or _log
     if getattr(server_module, "_b200_installed", False):
         return
+    frontend = _flag("B200_FRONTEND") if frontend is None else frontend
+    batch_windows = _flag("B200_BATCH_WINDOWS") if batch_windows is None else batch_windows
     orig_do = server_module._do_transcribe
     orig_load = getattr(server_module, "_load_model_sync", None)
+    orig_unload = getattr(server_module, "_unload_model_sync", None)
 
     def _do_transcribe(audio, sr, lang_code, return_timestamps, use_fast=False):
         fast = getattr(server_module, "_fast_model", None)
@@ -174,8 +277,46 @@ def install(server_module, log=None) -> None:
     if orig_load is not None:
         def _load_model_sync(*a, **kw):
             r = orig_load(*a, **kw)
-            try_load_b200_encoder(getattr(server_module, "model", None), getattr(server_module, "_fast_model", None), log=log)
+            models = (getattr(server_module, "model", None), getattr(server_module, "_fast_model", None))
+            try_load_b200_encoder(*models, log=log)
+            if frontend:
+                for m in models:
+                    if m is not None:
+                        try:
+                            install_frontend(m, log=log)
+                        except Exception as e:   # loader policy: report and carry on with the CPU extractor
+                            log.error(f"B200 log-mel frontend not installed: {e}")
             return r
 
         server_module._load_model_sync = _load_model_sync
+    if orig_unload is not None:
+        def _unload_model_sync(*a, **kw):
+            binding = getattr(server_module, "_b200_queue_binding", None)
+            if binding is not None:
+                binding.drain()
+            try:
+                return orig_unload(*a, **kw)
+            finally:
+                unload()   # model, fast model and aligner are gone (server.py:478-496): free their backends with them
+
+        server_module._unload_model_sync = _unload_model_sync
+    if subtitle_module is None:
+        import sys
+
+        subtitle_module = sys.modules.get("subtitle")
+    if subtitle_module is not None and hasattr(subtitle_module, "unload_aligner"):
+        orig_unload_aligner = subtitle_module.unload_aligner
+
+        def unload_aligner(*a, **kw):
+            al = getattr(subtitle_module, "_aligner", None)
+            if al is not None:
+                unload(al)
+            return orig_unload_aligner(*a, **kw)
+
+        subtitle_module.unload_aligner = unload_aligner
+    if batch_windows and hasattr(server_module, "_infer_queue"):
+        from .queue_binding import QueueBinding
+
+        server_module._b200_queue_binding = QueueBinding(server_module, log=log)
+        server_module._b200_queue_binding.install()
     server_module._b200_installed = True
