@@ -170,6 +170,23 @@ QASR_API int qasr_resample_pcm16(qasr_handle_t h, const int16_t* pcm16_dev, cons
                                  const double* taps, int n_taps, int16_t* out_dev, int64_t out_capacity, int64_t* out_offsets_out,
                                  void* stream);
 
+/* Upload normalisation of the HTTP path (src/server.py:867 hands (audio, sr) of any rate / channel count to the SDK, which turns it
+ * into mono float32 at 16 kHz): float32 frames with `channels` interleaved channels at orig_sr -> mono float32 at new_sr.  Defined as
+ * the reference's own spelling of that step in src/debug_audio.py:24-33: audio.mean(axis=1), then
+ * torchaudio.functional.resample(waveform, orig_sr, new_sr) = sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99.  The SDK's
+ * internal resampler is not available offline: pinned against torchaudio, unpinned against the SDK.
+ *   in_offsets         host int64 [n_streams + 1] in FRAMES (stream i = frames [in_offsets[i], in_offsets[i+1]), each `channels` floats)
+ *   taps               host float32 [new_sr / g][2 * width + orig_sr / g] (g = gcd; torchaudio's _get_sinc_resample_kernel layout), or
+ *                      NULL for the built-in design (the same float32 recipe, see qasr_resample_f32_taps)
+ *   out_dev            float32, stream i at [out_offsets_out[i], out_offsets_out[i + 1]), length ceil(n * new_sr / orig_sr) -- directly
+ *                      usable as the pcm_dev / clip_offsets of qasr_logmel and qasr_encode_pcm; out_capacity in samples */
+QASR_API int64_t qasr_resample_f32_len(int64_t n_in_frames, int orig_sr, int new_sr);
+QASR_API int qasr_resample_f32(qasr_handle_t h, const float* pcm_dev, const int64_t* in_offsets, int n_streams, int channels, int orig_sr,
+                               int new_sr, const float* taps, float* out_dev, int64_t out_capacity, int64_t* out_offsets_out, void* stream);
+/* The built-in resampling kernel on its own (pure host code, no GPU needed): writes [*n_phases][*n_taps] float32 into taps_out
+ * (may be NULL to query the sizes); *width = the zero padding torchaudio applies on the left. */
+QASR_API int qasr_resample_f32_taps(int orig_sr, int new_sr, float* taps_out, int64_t capacity, int* n_phases, int* n_taps, int* width);
+
 /* One WS window per stream: int16 16 kHz samples (+ pad_samples[i] int16 zeros appended: the 600 ms flush silence)
  * -> float32 / 32768 -> SOS band-pass in float64, zero initial state, cast to float32 -> zero-padded to min_samples
  * (replaces _transcribe_with_context's numpy prologue, src/server.py:1321-1338, and _telephony_bandpass, :26-29 =

@@ -19,6 +19,11 @@ Parity pinning
   ``res_type="soxr_hq"``); neither librosa nor soxr is installed here and there is no network.  The definition used
   instead is the polyphase Kaiser-windowed-sinc of ``scipy.signal.resample_poly`` (published algorithm, restated in
   ``resample_poly_f64``), and that restatement IS pinned against scipy's own output.
+* The upload normalisation (``normalize_upload`` = mono mean + ``resample_sinc_hann``) restates the reference's own spelling of
+  that step, src/debug_audio.py:24-33 (``audio.mean(axis=1)`` then ``torchaudio.functional.resample``: sinc_interp_hann,
+  lowpass_filter_width 6, rolloff 0.99 -- torchaudio/functional/functional.py:1305-1400, 1403-1430).  It is **pinned** against
+  the in-container torchaudio 2.11 (tests/test_oracle_prefrontend.py); the SDK's internal resampler behind src/server.py:867
+  stays unavailable offline.
 """
 
 from __future__ import annotations
@@ -144,3 +149,53 @@ def ws_window(pcm16: np.ndarray, orig_sr: int = TARGET_SR, pad_silence: bool = F
     if f.shape[0] < min_samples:
         f = np.concatenate([f, np.zeros(min_samples - f.shape[0], np.float32)])
     return f
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# torchaudio.functional.resample (sinc_interp_hann), restated in numpy float32 where torchaudio computes in float32
+def sinc_hann_kernel(orig_sr: int, new_sr: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """_get_sinc_resample_kernel for a float32 waveform (functional.py:1340-1400): every step in float32, in torch's order.
+    Returns (kernel float32 [new, 2 * width + orig], width) with orig / new reduced by their gcd."""
+    g = math.gcd(int(orig_sr), int(new_sr))
+    orig, new = int(orig_sr) // g, int(new_sr) // g
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    f32 = np.float32
+    idx = np.arange(-width, width + orig, dtype=f32)[None, :] / f32(orig)
+    t = np.arange(0, -new, -1, dtype=f32)[:, None] / f32(new) + idx
+    t = t * f32(base_freq)
+    t = np.clip(t, f32(-lowpass_filter_width), f32(lowpass_filter_width))
+    window = np.cos(t * f32(math.pi) / f32(lowpass_filter_width) / f32(2)) ** 2
+    t = t * f32(math.pi)
+    scale = f32(base_freq / orig)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        kernels = np.where(t == 0, f32(1.0), np.sin(t) / t).astype(f32)
+    kernels = kernels * (window * scale)
+    return kernels.astype(f32), width
+
+
+def resample_sinc_hann(x: np.ndarray, orig_sr: int, new_sr: int) -> np.ndarray:
+    """_apply_sinc_resample_kernel (functional.py:1403-1430): zero-pad (width, width + orig), correlate with stride orig, one phase
+    per output residue, cut to ceil(new * n / orig).  float32 taps and samples, products summed in float64."""
+    x = np.asarray(x, dtype=np.float32).reshape(-1)
+    if int(orig_sr) == int(new_sr):
+        return x.copy()
+    g = math.gcd(int(orig_sr), int(new_sr))
+    orig, new = int(orig_sr) // g, int(new_sr) // g
+    kern, width = sinc_hann_kernel(orig_sr, new_sr)
+    n = x.shape[0]
+    xp = np.concatenate([np.zeros(width, np.float32), x, np.zeros(width + orig, np.float32)]).astype(np.float64)
+    n_taps = kern.shape[1]
+    n_blocks = (xp.shape[0] - n_taps) // orig + 1
+    frames = np.lib.stride_tricks.sliding_window_view(xp, n_taps)[::orig][:n_blocks]      # [blocks, taps]
+    y = frames @ kern.astype(np.float64).T                                                  # [blocks, new]
+    target = -(-new * n // orig)
+    return y.reshape(-1)[:target].astype(np.float32)
+
+
+def normalize_upload(audio: np.ndarray, sr: int, target_sr: int = TARGET_SR) -> np.ndarray:
+    """src/debug_audio.py:24-33: (frames,) or (frames, channels) array as soundfile returns it -> mono float32 at target_sr."""
+    a = np.asarray(audio)
+    if a.ndim > 1:
+        a = a.astype(np.float64).mean(axis=1)
+    return resample_sinc_hann(a.astype(np.float32), sr, target_sr)

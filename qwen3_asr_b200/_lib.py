@@ -52,6 +52,10 @@ SIGNATURES = {
     "qasr_logmel_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, _I64P, _P]),
     "qasr_resample_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "qasr_resample_pcm16": (C.c_int, [_P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, _P, C.c_int64, _I64P, _P]),
+    "qasr_resample_f32_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "qasr_resample_f32": (C.c_int, [_P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _P, C.c_int64, _I64P, _P]),
+    "qasr_resample_f32_taps": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int)]),
     "qasr_ws_window": (C.c_int, [_P, _P, _I64P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_int, _P, C.c_int64,
                                  _I64P, _P]),
     "qasr_destroy": (None, [_P]),

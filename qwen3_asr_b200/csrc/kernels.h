@@ -42,6 +42,12 @@ cudaError_t launch_resample_pcm16(const int16_t* in, const RsStream* streams_dev
                                   const double* taps_dev, int n_taps, int half_len, int up, int down, int16_t* out, int num_sms,
                                   cudaStream_t stream);
 
+// float32 (interleaved channels) -> mono float32 at the new rate, torchaudio sinc_interp_hann (prefrontend.cu)
+void design_sinc_hann_kernel(int orig, int newf, std::vector<float>* kernel /*[newf][2 * width + orig]*/, int* width);
+cudaError_t launch_resample_f32(const float* in, const RsStream* streams_dev, int n_streams, long long max_out_len, int channels,
+                                const float* taps_dev, const int* lo_dev, int n_keep, int width, int orig, int newf, float* out,
+                                int num_sms, cudaStream_t stream);
+
 // ---- conv1 (elementwise.cu) ------------------------------------------------------------------
 struct ChunkDesc {
   long long mel_col0;  // first mel column of the chunk in the packed mel

@@ -1,6 +1,9 @@
 // WebSocket pre-frontend on the device: what the reference does to a WS audio
 // window on the CPU before the log-mel.
 //   resample_pcm16_kernel  <- src/server.py:32-42  _resample_pcm_bytes: int16 -> polyphase FIR resample -> astype(int16)
+//   resample_f32_kernel    <- the HTTP upload path's normalisation (src/server.py:867 -> SDK: mono mean, resample to 16 kHz,
+//                             float32), in the definition the reference itself spells out in src/debug_audio.py:24-33:
+//                             audio.mean(axis=1) -> torchaudio.functional.resample(sinc_interp_hann, width 6, rolloff 0.99)
 //   ws_window_kernel       <- src/server.py:1321-1338 + :26-29: [window] (+ flush silence) -> /32768 -> 300-3400 Hz
 //                             Butterworth SOS cascade (scipy sosfilt, float64, direct form II transposed) -> float32
 // Both are HBM-trivial (2-6 bytes per sample); the work is the float64 recursion, which is sequential in time.  It is
@@ -100,6 +103,59 @@ __global__ void __launch_bounds__(256) resample_pcm16_kernel(const int16_t* __re
   }
 }
 
+// torchaudio _apply_sinc_resample_kernel (functional.py): y[j * new + p] = sum_k kernel[p][k] * xpad[j * orig + k], xpad = x padded
+// by `width` zeros on the left and width + orig on the right, i.e. xpad[i] = x[i - width].  Only the taps inside the Hann window's
+// support are kept per phase (lo[p] .. lo[p] + n_keep): outside it torchaudio's float32 kernel holds cos^2 of a rounded pi / 2
+// times the sinc, |tap| < 1e-20.  Products of float32 values are exact in float64; the sum is accumulated in float64 and rounded
+// once (torch's conv1d accumulates in float32 in an unspecified order: its result scatters around this one by ~1e-7).
+// channels > 1: the mono sample is float32(float64 sum over the interleaved channels / channels) -- numpy's audio.mean(axis=1)
+// on the float64 array soundfile returns, followed by the .float() cast (debug_audio.py:24-31).
+__global__ void __launch_bounds__(256) resample_f32_kernel(const float* __restrict__ in, const RsStream* __restrict__ streams, int channels,
+                                                           const float* __restrict__ taps, const int* __restrict__ lo, int n_keep,
+                                                           int width, int orig, int newf, float* __restrict__ out) {
+  const RsStream st = streams[blockIdx.y];
+  const float* __restrict__ x = in + st.in_off * channels;
+  float* __restrict__ y = out + st.out_off;
+  const double inv_c = 1.0 / channels;
+  for (long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; n < st.out_len;
+       n += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long j = n / newf;
+    const int p = static_cast<int>(n - j * newf);
+    const float* __restrict__ tp = taps + static_cast<long long>(p) * n_keep;
+    const long long i0 = j * orig + lo[p] - width;   // input frame of the first kept tap
+    double acc = 0.0;
+    for (int k = 0; k < n_keep; ++k) {
+      const long long i = i0 + k;
+      if (i < 0 || i >= st.in_len) continue;
+      float xv;
+      if (channels == 1) {
+        xv = __ldg(x + i);
+      } else {
+        double s = 0.0;
+        for (int c = 0; c < channels; ++c) s = __dadd_rn(s, static_cast<double>(__ldg(x + i * channels + c)));
+        xv = static_cast<float>(s * inv_c);
+      }
+      acc = fma(static_cast<double>(__ldg(tp + k)), static_cast<double>(xv), acc);
+    }
+    y[n] = static_cast<float>(acc);
+  }
+}
+
+// orig == new: torchaudio returns the waveform unchanged; only the channel mean remains
+__global__ void __launch_bounds__(256) downmix_f32_kernel(const float* __restrict__ in, const RsStream* __restrict__ streams, int channels,
+                                                          float* __restrict__ out) {
+  const RsStream st = streams[blockIdx.y];
+  const float* __restrict__ x = in + st.in_off * channels;
+  float* __restrict__ y = out + st.out_off;
+  const double inv_c = 1.0 / channels;
+  for (long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; n < st.out_len;
+       n += static_cast<long long>(gridDim.x) * blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < channels; ++c) s = __dadd_rn(s, static_cast<double>(__ldg(x + n * channels + c)));
+    y[n] = channels == 1 ? __ldg(x + n) : static_cast<float>(s * inv_c);
+  }
+}
+
 double bessel_i0(double x) {
   const double q = (x / 2.0) * (x / 2.0);
   double term = 1.0, s = 1.0;
@@ -132,6 +188,39 @@ void design_resample_taps(int up, int down, std::vector<double>* taps, int* half
   }
   for (int k = 0; k < n; ++k) (*taps)[k] = (*taps)[k] / sum * up;
   *half_len = hl;
+}
+
+// torchaudio.functional._get_sinc_resample_kernel(orig, new, gcd, lowpass_filter_width = 6, rolloff = 0.99, "sinc_interp_hann",
+// dtype = float32) restated operation by operation IN FLOAT32, as torchaudio evaluates it for a float32 waveform (functional.py:
+// 1340-1400): kernel[p][k] for p < new, k < 2 * width + orig.  Differences to torch are confined to its vectorised sinf / cosf
+// (<= 1 ulp each).  orig / new are already divided by their gcd.
+void design_sinc_hann_kernel(int orig, int newf, std::vector<float>* kernel, int* width_out) {
+  const int lpw = 6;
+  const double rolloff = 0.99;
+  double base_freq = static_cast<double>(orig < newf ? orig : newf);
+  base_freq *= rolloff;
+  const int width = static_cast<int>(std::ceil(lpw * orig / base_freq));
+  const int n_taps = 2 * width + orig;
+  const float base_f = static_cast<float>(base_freq);
+  const float scale_f = static_cast<float>(base_freq / orig);
+  const float pi_f = static_cast<float>(3.14159265358979323846);
+  kernel->assign(static_cast<size_t>(newf) * n_taps, 0.f);
+  for (int p = 0; p < newf; ++p) {
+    const float tp = static_cast<float>(-p) / static_cast<float>(newf);
+    for (int k = 0; k < n_taps; ++k) {
+      const float idx = static_cast<float>(k - width) / static_cast<float>(orig);
+      float t = tp + idx;
+      t *= base_f;
+      t = std::fmin(std::fmax(t, -static_cast<float>(lpw)), static_cast<float>(lpw));
+      const float c = cosf(t * pi_f / static_cast<float>(lpw) / 2.0f);
+      const float window = c * c;
+      t *= pi_f;
+      float v = t == 0.f ? 1.0f : sinf(t) / t;
+      v *= window * scale_f;
+      (*kernel)[static_cast<size_t>(p) * n_taps + k] = v;
+    }
+  }
+  *width_out = width;
 }
 
 // Samples after which the cascade has forgotten its initial state to 1e-18: from the largest pole radius of the sections.
@@ -184,6 +273,19 @@ cudaError_t launch_resample_pcm16(const int16_t* in, const RsStream* streams_dev
   const long long want = (max_out_len + 255) / 256;
   dim3 grid(static_cast<unsigned int>(want < 4LL * num_sms ? want : 4LL * num_sms), n_streams);
   resample_pcm16_kernel<<<grid, 256, 0, stream>>>(in, streams_dev, taps_dev, n_taps, half_len, up, down, out);
+  return cudaGetLastError();
+}
+
+// taps_dev: compact [newf][n_keep] float32, lo_dev: [newf] first kept tap of every phase
+cudaError_t launch_resample_f32(const float* in, const RsStream* streams_dev, int n_streams, long long max_out_len, int channels,
+                                const float* taps_dev, const int* lo_dev, int n_keep, int width, int orig, int newf, float* out,
+                                int num_sms, cudaStream_t stream) {
+  if (n_streams == 0 || max_out_len == 0) return cudaSuccess;
+  if (n_streams > 65535 || channels < 1) return cudaErrorInvalidValue;
+  const long long want = (max_out_len + 255) / 256;
+  dim3 grid(static_cast<unsigned int>(want < 8LL * num_sms ? want : 8LL * num_sms), n_streams);
+  if (orig == newf) downmix_f32_kernel<<<grid, 256, 0, stream>>>(in, streams_dev, channels, out);
+  else resample_f32_kernel<<<grid, 256, 0, stream>>>(in, streams_dev, channels, taps_dev, lo_dev, n_keep, width, orig, newf, out);
   return cudaGetLastError();
 }
 

@@ -620,7 +620,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->max_tokens = std::max(h->max_tokens, h->chunks_per_window * kTokPerChunk);
   // experiment / checker switches: unknown values are an error, not a silent default
   const int v_simt = env_choice("QASR_DEBUG_SIMT", {"0", "1"});
-  const int v_ln = env_choice("QASR_LN", {"fold", "unfused", "epilogue_stats"});
+  const int v_ln = env_choice("QASR_LN", {"stats_kernel", "unfused", "epilogue_stats"});  // stats_kernel (the default): folded LayerNorm, statistics pass
   const int v_att = env_choice("QASR_ATTENTION", {"tc", "mma_sync"});
   const int v_keep = env_choice("QASR_DEBUG_KEEP", {"0", "1"});
   const int v_pdl = env_choice("QASR_PDL", {"1", "0"});
@@ -1176,6 +1176,110 @@ int qasr_resample_pcm16(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t
               launch_resample_pcm16(pcm16_dev, reinterpret_cast<const RsStream*>(st->dev), n_streams, max_out,
                                     reinterpret_cast<const double*>(st->dev + desc_bytes), n_taps, half_len, up, down, out_dev,
                                     h->num_sms, stream));
+  QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
+  st->in_flight = true;
+  return stream_leave(h, stream);
+}
+
+namespace {
+int gcd_int(int a, int b) {
+  while (b != 0) { const int t = a % b; a = b; b = t; }
+  return a;
+}
+}  // namespace
+
+int64_t qasr_resample_f32_len(int64_t n_in, int orig_sr, int new_sr) {
+  if (n_in <= 0 || orig_sr <= 0 || new_sr <= 0) return 0;
+  const int g = gcd_int(orig_sr, new_sr);
+  const int64_t o = orig_sr / g, n = new_sr / g;
+  return (n * n_in + o - 1) / o;   // torch.ceil(new_freq * length / orig_freq)
+}
+
+int qasr_resample_f32_taps(int orig_sr, int new_sr, float* taps_out, int64_t capacity, int* n_phases, int* n_taps, int* width) {
+  QASR_REQUIRE(orig_sr > 0 && new_sr > 0 && n_phases != nullptr && n_taps != nullptr && width != nullptr, "qasr_resample_f32_taps: bad argument");
+  const int g = gcd_int(orig_sr, new_sr);
+  const int o = orig_sr / g, n = new_sr / g;
+  QASR_REQUIRE(o <= 4096 && n <= 4096, "qasr_resample_f32_taps: reduced rates must be <= 4096");
+  std::vector<float> k;
+  int w = 0;
+  design_sinc_hann_kernel(o, n, &k, &w);
+  *n_phases = n;
+  *n_taps = 2 * w + o;
+  *width = w;
+  if (taps_out != nullptr) {
+    QASR_REQUIRE(capacity >= static_cast<int64_t>(k.size()), "qasr_resample_f32_taps: capacity too small, need " + std::to_string(k.size()));
+    std::memcpy(taps_out, k.data(), k.size() * sizeof(float));
+  }
+  return 0;
+}
+
+int qasr_resample_f32(qasr_handle_t h, const float* pcm_dev, const int64_t* in_offsets, int n_streams, int channels, int orig_sr, int new_sr,
+                      const float* taps, float* out_dev, int64_t out_capacity, int64_t* out_offsets_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && in_offsets != nullptr && out_offsets_out != nullptr && n_streams >= 0, "qasr_resample_f32: bad argument");
+  QASR_REQUIRE(channels >= 1 && channels <= 64, "qasr_resample_f32: channels must be in [1, 64]");
+  QASR_REQUIRE(orig_sr > 0 && new_sr > 0, "qasr_resample_f32: sample rates must be positive");
+  QASR_REQUIRE(n_streams <= 65535, "qasr_resample_f32: at most 65535 streams per call");
+  const int g = gcd_int(orig_sr, new_sr);
+  const int orig = orig_sr / g, newf = new_sr / g;
+  QASR_REQUIRE(orig <= 4096 && newf <= 4096, "qasr_resample_f32: reduced rates must be <= 4096 (e.g. 44100 -> 16000 is 441 -> 160)");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  out_offsets_out[0] = 0;
+  long long max_out = 0;
+  for (int i = 0; i < n_streams; ++i) {
+    const int64_t n = in_offsets[i + 1] - in_offsets[i];
+    QASR_REQUIRE(n >= 0, "qasr_resample_f32: offsets must be non-decreasing");
+    const int64_t m = orig == newf ? n : qasr_resample_f32_len(n, orig, newf);
+    out_offsets_out[i + 1] = out_offsets_out[i] + m;
+    max_out = std::max<long long>(max_out, m);
+  }
+  QASR_REQUIRE(out_offsets_out[n_streams] <= out_capacity, "qasr_resample_f32: out_capacity too small");
+  if (n_streams == 0 || max_out == 0) return 0;
+  QASR_REQUIRE(pcm_dev != nullptr && out_dev != nullptr, "qasr_resample_f32: null buffer");
+  // per-phase support of the Hann window: keep taps [lo[p], lo[p] + n_keep) of the full kernel (see resample_f32_kernel)
+  std::vector<float> full, compact;
+  std::vector<int> lo(newf, 0);
+  int width = 0, n_keep = 1, n_taps = 1;
+  if (orig != newf) {
+    if (taps == nullptr) {
+      design_sinc_hann_kernel(orig, newf, &full, &width);
+      taps = full.data();
+    } else {
+      double base = static_cast<double>(std::min(orig, newf));
+      base *= 0.99;
+      width = static_cast<int>(std::ceil(6 * orig / base));
+    }
+    n_taps = 2 * width + orig;
+    const double support = 6.0 * orig / (0.99 * std::min(orig, newf));   // |k - width - p * orig / new| < support (in input samples)
+    std::vector<int> hi(newf, 0);
+    n_keep = 0;
+    for (int p = 0; p < newf; ++p) {
+      const double centre = width + static_cast<double>(p) * orig / newf;
+      lo[p] = std::max(0, static_cast<int>(std::floor(centre - support)) - 1);
+      hi[p] = std::min(n_taps, static_cast<int>(std::ceil(centre + support)) + 2);
+      n_keep = std::max(n_keep, hi[p] - lo[p]);
+    }
+    compact.assign(static_cast<size_t>(newf) * n_keep, 0.f);
+    for (int p = 0; p < newf; ++p)
+      for (int k = lo[p]; k < hi[p]; ++k) compact[static_cast<size_t>(p) * n_keep + (k - lo[p])] = taps[static_cast<size_t>(p) * n_taps + k];
+  }
+  const size_t o_desc = 0;
+  const size_t o_lo = align_up(sizeof(RsStream) * static_cast<size_t>(n_streams), 16);
+  const size_t o_taps = align_up(o_lo + sizeof(int) * lo.size(), 16);
+  const size_t total = o_taps + sizeof(float) * std::max<size_t>(compact.size(), 1);
+  Staging* st = nullptr;
+  if (stream_enter(h, stream) != 0) return 2;
+  if (staging_acquire(h, total, &st) != 0) return 2;
+  RsStream* d = reinterpret_cast<RsStream*>(st->host + o_desc);
+  for (int i = 0; i < n_streams; ++i)
+    d[i] = {in_offsets[i], in_offsets[i + 1] - in_offsets[i], out_offsets_out[i], out_offsets_out[i + 1] - out_offsets_out[i]};
+  std::memcpy(st->host + o_lo, lo.data(), sizeof(int) * lo.size());
+  if (!compact.empty()) std::memcpy(st->host + o_taps, compact.data(), sizeof(float) * compact.size());
+  QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
+  QASR_LAUNCH(h, "resample_f32", 4.0 * static_cast<double>((in_offsets[n_streams] - in_offsets[0]) * channels + out_offsets_out[n_streams]), stream,
+              launch_resample_f32(pcm_dev, reinterpret_cast<const RsStream*>(st->dev + o_desc), n_streams, max_out, channels,
+                                  reinterpret_cast<const float*>(st->dev + o_taps), reinterpret_cast<const int*>(st->dev + o_lo), n_keep,
+                                  width, orig, newf, out_dev, h->num_sms, stream));
   QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
   st->in_flight = true;
   return stream_leave(h, stream);

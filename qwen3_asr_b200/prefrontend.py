@@ -6,6 +6,8 @@ The reference prepares every WS window on the CPU before the SDK sees it (SURVEY
 * ``_telephony_bandpass(audio, sr)``           -- src/server.py:26-29
 * the prologue of ``_transcribe_with_context``  -- src/server.py:1321-1338: [overlap + chunk] (+ 600 ms flush
   silence) -> int16 -> float32 / 32768 -> band-pass
+* the normalisation of an HTTP upload (src/server.py:867 hands ``(audio, sr)`` to the SDK): mono mean + resample to 16 kHz,
+  in the reference's own spelling of it, src/debug_audio.py:24-33 (``audio.mean(axis=1)``, ``torchaudio.functional.resample``)
 
 ``B200PreFrontend`` keeps those names and argument meanings, but takes a *batch* of streams and leaves the result on
 the GPU, packed exactly as ``B200AudioEncoder.encode_pcm_packed`` / ``logmel_packed`` expect it, so PCM bytes in ->
@@ -99,6 +101,51 @@ class B200PreFrontend:
         dev, offs = self._pack_int16([pcm_bytes])
         out, _ = self.resample_pcm16_packed(dev, offs, orig_sr)
         return out.cpu().numpy().tobytes()
+
+    # ---- upload normalisation: any rate, any channel count -> mono float32 16 kHz -----------------------------------
+    def normalize_audio(self, clips: Sequence["np.ndarray | torch.Tensor"], sr: int, target_sr: int = TARGET_SR,
+                        taps: np.ndarray | None = None):
+        """clips: arrays shaped (frames,) or (frames, channels) -- what ``soundfile.read`` returns -- all at ``sr`` and with the
+        same channel count.  Returns (mono float32 device tensor of clips back to back at target_sr, offsets): ready for
+        ``encode_pcm_packed`` / ``logmel_packed``.  Channel mean and sinc_interp_hann resampling run on the device."""
+        arrs = [np.asarray(c.cpu() if isinstance(c, torch.Tensor) else c) for c in clips]
+        channels = {1 if a.ndim == 1 else int(a.shape[1]) for a in arrs}
+        if len(channels) > 1:
+            raise QasrError(f"normalize_audio: clips of one call must share a channel count, got {sorted(channels)}")
+        ch = channels.pop() if channels else 1
+        offs = np.zeros(len(arrs) + 1, dtype=np.int64)
+        for i, a in enumerate(arrs):
+            offs[i + 1] = offs[i] + a.shape[0]
+        host = torch.empty(int(offs[-1]) * ch, dtype=torch.float32, pin_memory=True)
+        for i, a in enumerate(arrs):
+            host[int(offs[i]) * ch:int(offs[i + 1]) * ch] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1))
+        return self.resample_f32_packed(host.to(self.enc.tdev, non_blocking=True), offs, ch, sr, target_sr, taps)
+
+    def resample_f32_packed(self, pcm: torch.Tensor, offsets: np.ndarray, channels: int, orig_sr: int, target_sr: int = TARGET_SR,
+                            taps: np.ndarray | None = None):
+        """pcm: float32 device tensor, frames of ``channels`` interleaved samples, streams back to back; offsets in frames."""
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        if channels == 1 and int(orig_sr) == int(target_sr):
+            return pcm, offsets
+        total = int(sum(self.lib.qasr_resample_f32_len(int(offsets[i + 1] - offsets[i]), int(orig_sr), int(target_sr)) for i in range(n)))
+        out = torch.empty(total, dtype=torch.float32, device=self.enc.tdev)
+        out_offs = np.zeros(n + 1, dtype=np.int64)
+        tp = None
+        if taps is not None:
+            taps = np.ascontiguousarray(taps, dtype=np.float32)
+            tp = taps.ctypes.data_as(C.POINTER(C.c_float))
+        check(self.lib, self.lib.qasr_resample_f32(self.enc._h, C.c_void_p(pcm.data_ptr()), offsets.ctypes.data_as(_lib._I64P), n,
+                                                   int(channels), int(orig_sr), int(target_sr), tp, C.c_void_p(out.data_ptr()), total,
+                                                   out_offs.ctypes.data_as(_lib._I64P), self.enc._stream()),
+              "qasr_resample_f32")
+        return out, out_offs
+
+    def encode_uploads(self, clips: Sequence, sr: int):
+        """(audio, sr) uploads -> (bf16 hidden states, token_lens): normalise, log-mel and encode without leaving the GPU."""
+        pcm, offs = self.normalize_audio(clips, sr)
+        return self.enc.encode_pcm_packed(pcm, offs)
 
     # ---- int16 -> float -> band-pass ------------------------------------------------------------------------------
     def ws_window_packed(self, pcm16: torch.Tensor, offsets: np.ndarray, pad_silence: "Sequence[bool] | None" = None,

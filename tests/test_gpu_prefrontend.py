@@ -180,3 +180,74 @@ def test_window_batcher_over_the_real_encoder(pre):
         alone, _ = pre.encode_windows([wins[i]], 16000, pad_silence=[flush[i]])
         torch.cuda.synchronize()
         assert torch.equal(outs[i], alone), i
+
+
+# ---- row a2: upload normalisation (any rate, any channel count -> mono float32 16 kHz) -----------------------------------
+@pytest.mark.parametrize("sr", [8000, 22050, 44100, 48000, 11025, 16000])
+def test_resample_f32_vs_torchaudio(pre, sr):
+    """within 1e-6 absolute of torchaudio.functional.resample (sinc_interp_hann, width 6, rolloff 0.99 -- the
+    definition src/debug_audio.py:28-33 uses), ragged batch, built-in taps and torchaudio's own kernel handed over the ABI."""
+    import math
+
+    import torchaudio.functional as AF
+    from torchaudio.functional.functional import _get_sinc_resample_kernel
+
+    rng = np.random.default_rng(sr)
+    lens = [sr * 2 + 37, 1, sr // 3, 5 * sr + 1234, 0, 441]
+    clips = [(0.5 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * 700.0 * np.arange(n) / sr)).astype(np.float32) for n in lens]
+    out, offs = pre.normalize_audio(clips, sr)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for i, c in enumerate(clips):
+        want = AF.resample(torch.from_numpy(c)[None], sr, 16000)[0].numpy() if len(c) else np.zeros(0, np.float32)
+        got = out[offs[i]:offs[i + 1]]
+        assert got.shape == want.shape, (i, got.shape, want.shape)
+        if len(want):
+            assert np.abs(got - want).max() <= 1e-6, (sr, i, np.abs(got - want).max())
+    if sr != 16000:
+        k, _ = _get_sinc_resample_kernel(sr, 16000, math.gcd(sr, 16000), dtype=torch.float32)
+        out2, offs2 = pre.normalize_audio(clips, sr, taps=k.numpy()[:, 0, :])
+        torch.cuda.synchronize()
+        assert offs2.tolist() == offs.tolist()
+        want = np.concatenate([AF.resample(torch.from_numpy(c)[None], sr, 16000)[0].numpy() for c in clips if len(c)])
+        assert np.abs(out2.cpu().numpy() - want).max() <= 5e-7     # same taps: only the summation order differs
+
+
+def test_stereo_upload_is_debug_audio_py(pre):
+    """src/debug_audio.py:24-33 verbatim on the CPU (float64 mean over channels, .float(), torchaudio resample) vs the device path."""
+    import torchaudio.functional as AF
+
+    from oracle import prefrontend as opf
+
+    rng = np.random.default_rng(9)
+    clips = [rng.uniform(-1, 1, size=(n, 2)) for n in (44100, 30011)]
+    out, offs = pre.normalize_audio(clips, 44100)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for i, a in enumerate(clips):
+        mono = a.astype(np.float32).astype(np.float64).mean(axis=1)     # the device receives float32 samples
+        want = AF.resample(torch.from_numpy(mono).unsqueeze(0).float(), 44100, 16000).squeeze(0).numpy()
+        got = out[offs[i]:offs[i + 1]]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-6
+        assert np.abs(got - opf.normalize_upload(a.astype(np.float32), 44100)).max() <= 1e-6
+    # 16 kHz stereo: only the channel mean
+    out, offs = pre.normalize_audio([clips[0]], 16000)
+    want = clips[0].astype(np.float32).astype(np.float64).mean(axis=1).astype(np.float32)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_upload_to_tokens_stays_on_the_device(pre):
+    """44.1 kHz stereo upload -> normalise -> log-mel -> encoder equals encoding the torchaudio-normalised clip."""
+    import torchaudio.functional as AF
+
+    rng = np.random.default_rng(10)
+    t = np.arange(3 * 44100) / 44100.0
+    a = np.stack([0.4 * np.sin(2 * np.pi * 330 * t) + 0.05 * rng.standard_normal(len(t)), 0.3 * np.sin(2 * np.pi * 550 * t)], axis=1)
+    hid, toks = pre.encode_uploads([a], 44100)
+    mono = a.astype(np.float32).astype(np.float64).mean(axis=1)
+    ref_pcm = AF.resample(torch.from_numpy(mono).unsqueeze(0).float(), 44100, 16000).squeeze(0).numpy()
+    hid2, toks2 = pre.enc.encode_pcm([ref_pcm])
+    torch.cuda.synchronize()
+    assert toks.tolist() == toks2.tolist() == [39]
+    a_, b_ = hid.float().cpu().numpy(), hid2.float().cpu().numpy()
+    assert np.abs(a_ - b_).max() <= 2e-2 * max(1.0, np.abs(b_).max()) and (a_ != b_).mean() < 0.05

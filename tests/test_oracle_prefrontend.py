@@ -57,3 +57,63 @@ def test_ws_window_layout():
     assert np.abs(w[3000:3100]).max() > 0
     raw = pf.ws_window(x, 16000, bandpass=False, min_samples=0)
     assert np.array_equal(raw, x.astype(np.float32) / 32768.0)
+
+
+# ---- upload normalisation (row a2): torchaudio sinc_interp_hann, the definition src/debug_audio.py:24-33 spells out
+RATES = [8000, 11025, 22050, 32000, 44100, 48000]
+
+
+def _wave(n, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    return (0.3 * rng.standard_normal(n) + 0.4 * np.sin(2 * np.pi * 523.0 * t) * np.sin(2 * np.pi * 3 * t)).astype(np.float32)
+
+
+@pytest.mark.parametrize("sr", RATES)
+def test_sinc_hann_restatement_vs_torchaudio(sr):
+    import torch
+    import torchaudio.functional as AF
+
+    x = _wave(sr // 2 + 37, sr)
+    want = AF.resample(torch.from_numpy(x)[None], sr, 16000)[0].numpy()
+    got = pf.resample_sinc_hann(x, sr, 16000)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.abs(got - want).max() <= 1e-6, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("sr", RATES)
+def test_builtin_resample_taps_match_torchaudios_kernel(sr):
+    """qasr_resample_f32_taps (pure host code of the library): the float32 recipe of _get_sinc_resample_kernel, <= 2 ulp per tap."""
+    import ctypes as C
+    import math
+
+    import torch
+    from torchaudio.functional.functional import _get_sinc_resample_kernel
+
+    from qwen3_asr_b200 import load_library
+
+    lib = load_library()
+    k, w = _get_sinc_resample_kernel(sr, 16000, math.gcd(sr, 16000), dtype=torch.float32)
+    k = k.numpy()[:, 0, :]
+    n_ph, n_taps, width = C.c_int(), C.c_int(), C.c_int()
+    assert lib.qasr_resample_f32_taps(sr, 16000, None, 0, C.byref(n_ph), C.byref(n_taps), C.byref(width)) == 0
+    assert (n_ph.value, n_taps.value, width.value) == (k.shape[0], k.shape[1], w)
+    buf = np.zeros(k.shape, np.float32)
+    assert lib.qasr_resample_f32_taps(sr, 16000, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size, C.byref(n_ph), C.byref(n_taps),
+                                      C.byref(width)) == 0
+    assert np.abs(buf - k).max() <= 2.5e-7 * np.abs(k).max()
+    ko, wo = pf.sinc_hann_kernel(sr, 16000)
+    assert wo == w and np.abs(ko - k).max() <= 2.5e-7 * np.abs(k).max()
+    assert lib.qasr_resample_f32_len(sr // 2 + 37, sr, 16000) == -(-(16000 * (sr // 2 + 37)) // sr)
+
+
+def test_normalize_upload_is_debug_audio_py():
+    import torch
+    import torchaudio.functional as AF
+
+    rng = np.random.default_rng(3)
+    stereo = rng.uniform(-1, 1, size=(30011, 2))           # soundfile hands back float64 [frames, channels]
+    mono = stereo.mean(axis=1)
+    want = AF.resample(torch.from_numpy(mono).unsqueeze(0).float(), 44100, 16000).squeeze(0).numpy()   # debug_audio.py:24-33 verbatim
+    got = pf.normalize_upload(stereo, 44100)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-6
