@@ -232,21 +232,44 @@ def _attention(w, prefix: str, h: torch.Tensor, wins, cfg: EncoderConfig, emulat
     return _rnd(_linear(out, w[prefix + "out_proj.weight"], w[prefix + "out_proj.bias"], fp8), emulate_bf16)
 
 
+class oracle_device_fp32:
+    """Context manager: true float32 matmuls / convolutions on a CUDA device (TF32 off) while the oracle runs there."""
+
+    def __enter__(self):
+        self._m, self._c = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+        self._p = torch.get_float32_matmul_precision()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.set_float32_matmul_precision("highest")
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self._m, self._c
+        torch.set_float32_matmul_precision(self._p)
+        return False
+
+
 @torch.no_grad()
-def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, return_intermediate: bool = False, fp8=None):
+def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, return_intermediate: bool = False, fp8=None, device=None):
     """mels: list of float32 [128, T_i] (already at the precision the tower sees,
     e.g. rounded through bf16).  Returns (hidden [sum tokens, output_dim] float32,
     token_lens list).  ``emulate_bf16`` rounds every module output through bf16,
     the reference deployment's rounding points.
     ``fp8``: None, "per_tensor" or "per_row" -- every nn.Linear (conv_out, q/k/v/out_proj, fc1, fc2, proj1, proj2)
     through ``linear_fp8``; the convolutions stay as they are (torchao's default filter).
-    Per-tensor activation scales are taken over the whole call, as torchao takes them over the tensor it is handed."""
+    Per-tensor activation scales are taken over the whole call, as torchao takes them over the tensor it is handed.
+    ``device``: where the same float32 torch ops run (default: where the weights are, normally the CPU).  On a CUDA device the
+    caller must have TF32 switched off (``oracle_device_fp32``) -- it is the same restatement, only evaluated faster, so that
+    whole batches at the real model sizes can be checked."""
     if fp8 is not None:
         emulate_bf16 = True
-    mels = [torch.as_tensor(np.asarray(m), dtype=torch.float32) for m in mels]
+    if device is None:
+        device = next(iter(w.values())).device
+    device = torch.device(device)
+    mels = [torch.as_tensor(np.asarray(m.cpu() if isinstance(m, torch.Tensor) else m), dtype=torch.float32).to(device) for m in mels]
     cf = cfg.chunk_frames
     d = cfg.d_model
-    pe = sinusoid_table(cfg.max_source_positions, d)
+    pe = sinusoid_table(cfg.max_source_positions, d).to(device)
     pe = _rnd(pe, emulate_bf16)
 
     # --- conv stem per chunk (all 100-frame-padded chunks batched; short lone clips alone)
@@ -256,7 +279,7 @@ def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, ret
         t = m.shape[1]
         toks = []
         for (s0, valid, padded) in chunk_plan(t, cf):
-            ch = torch.zeros(cfg.num_mel_bins, padded)
+            ch = torch.zeros(cfg.num_mel_bins, padded, device=device)
             ch[:, :valid] = m[:, s0 : s0 + valid]
             if padded == cf:
                 full_owner.append((ci, len(toks), valid))
@@ -283,7 +306,7 @@ def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, ret
             c, f, tw = y.shape
             emb_in.append(y.permute(2, 0, 1).reshape(tw, c * f))  # index c*16+f (:735-736)
             emb_meta.append((tw, valid))
-    emb_all = _rnd(_linear(torch.cat(emb_in, dim=0), w["conv_out.weight"], None, fp8), emulate_bf16) if emb_in else torch.zeros(0, d)
+    emb_all = _rnd(_linear(torch.cat(emb_in, dim=0), w["conv_out.weight"], None, fp8), emulate_bf16) if emb_in else torch.zeros(0, d, device=device)
     rows, token_lens = [], []
     pos, mi = 0, 0
     for toks in per_clip_tokens:
@@ -297,7 +320,7 @@ def encoder_forward(w, cfg: EncoderConfig, mels, emulate_bf16: bool = False, ret
             rows.append(emb[:nv])
             n_tok += nv
         token_lens.append(n_tok)
-    x = torch.cat(rows, dim=0) if rows else torch.zeros(0, d)
+    x = torch.cat(rows, dim=0) if rows else torch.zeros(0, d, device=device)
     inter = {"embed": x.clone()} if return_intermediate else None
 
     wins = []

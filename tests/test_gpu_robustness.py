@@ -34,20 +34,23 @@ def _clips():
 def test_a_nan_clip_does_not_leak_into_its_batch_neighbours(tiny):
     """The tcgen05 attention multiplies P V over keys rounded up to 16: V rows past a window's end (the NEXT clip's rows, or stale
     rows of an earlier, larger batch) are zeroed on chip, so a NaN / Inf there cannot turn 0 * x into NaN.  Every clean clip must
-    come out bit-identical to the batch without the bad clip, in this call and in the (smaller) calls that follow."""
+    come out bit-identical to the batch without the bad clip, in this call and in the (smaller) calls that follow.  Poisoned at the
+    feature level (non-finite log-mel columns reach the encoder as they are) and at the PCM level (the log-mel clamp is an fmax,
+    which drops NaN: the bad clip may even come out finite -- the neighbours must not move either way)."""
     _, _, enc = tiny
     clips = _clips()
-    ref, toks = enc.encode_pcm(clips)
+    mel, flens = enc.logmel(clips)
+    ref = enc.encode(mel, flens).clone()
+    toks = enc.last_token_lens.copy()
     torch.cuda.synchronize()
-    ref = ref.clone()
     assert torch.isfinite(ref.float()).all()
     offs = np.concatenate([[0], np.cumsum(toks)])
-    for bad_i, poison in ((1, np.nan), (0, np.inf), (2, np.nan)):
-        bad = [c.copy() for c in clips]
-        bad[bad_i][1000:1100] = poison
-        out, toks2 = enc.encode_pcm(bad)
+    cols = np.concatenate([[0], np.cumsum(flens)])
+    for bad_i, poison in ((1, float("nan")), (0, float("inf")), (2, float("nan")), (3, float("-inf"))):
+        bad = mel.clone()
+        bad[:, int(cols[bad_i]) + 3:int(cols[bad_i]) + 9] = poison
+        out = enc.encode(bad, flens)
         torch.cuda.synchronize()
-        assert toks2.tolist() == toks.tolist()
         for i in range(len(clips)):
             got, want = out[offs[i]:offs[i + 1]], ref[offs[i]:offs[i + 1]]
             if i == bad_i:
@@ -55,9 +58,19 @@ def test_a_nan_clip_does_not_leak_into_its_batch_neighbours(tiny):
             else:
                 assert torch.equal(got, want), f"clip {i} changed when clip {bad_i} was poisoned"
         # a later, smaller batch reuses the workspace rows the poisoned clip left behind
-        small, _ = enc.encode_pcm([clips[0]])
+        small = enc.encode(mel[:, :int(cols[1])].contiguous(), flens[:1])
         torch.cuda.synchronize()
         assert torch.equal(small, ref[offs[0]:offs[1]])
+    ref_pcm, _ = enc.encode_pcm(clips)
+    for bad_i, poison in ((1, np.nan), (0, np.inf)):
+        bad = [c.copy() for c in clips]
+        bad[bad_i][1000:1100] = poison
+        out, toks2 = enc.encode_pcm(bad)
+        torch.cuda.synchronize()
+        assert toks2.tolist() == toks.tolist()
+        for i in range(len(clips)):
+            if i != bad_i:
+                assert torch.equal(out[offs[i]:offs[i + 1]], ref_pcm[offs[i]:offs[i + 1]]), f"clip {i} changed when clip {bad_i}'s PCM was poisoned"
 
 
 def test_an_empty_window_does_not_fail_its_batch(tiny):
