@@ -95,11 +95,13 @@ class B200AudioEncoder:
         h = C.c_void_p()
         check(self.lib, self.lib.qasr_create(C.byref(self.cfg), self.device, C.byref(h)), "qasr_create")
         self._h = h
+        self.weight_bytes = 0   # bf16 bytes of the parameters handed over: what one forward must at least read from HBM
         try:
             for name, w in weights.items():
                 if "positional_embedding" in name and name != "positional_embedding":
                     continue
                 self._set_weight(name, w)
+                self.weight_bytes += 2 * int(np.prod(tuple(w.shape)))
             if "positional_embedding" not in weights:
                 self._set_weight("positional_embedding", sinusoid_table(13, self.d_model))
             check(self.lib, self.lib.qasr_finalize(self._h), "qasr_finalize")

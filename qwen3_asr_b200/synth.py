@@ -101,3 +101,45 @@ def lpt_assign(frames, n_ranks: int):
     for b in bins:
         b.sort()
     return bins
+
+
+# ---- BASELINE.json configs as product-side synthetic workloads (bench.py --config c1 .. c5; definitions: SURVEY.md section 8(d)) ----
+def noise_clip(n: int, seed: int = 0, amplitude: float = 0.1) -> np.ndarray:
+    """C1: x = 0.1 * default_rng(seed).standard_normal(N), float32."""
+    return (amplitude * np.random.default_rng(seed).standard_normal(n)).astype(np.float32)
+
+
+def workload_c1(seed: int = 0):
+    """BASELINE.json configs[0]: one 5 s clip, batch 1 (0.6B dims)."""
+    return [noise_clip(80000, seed)]
+
+
+def workload_c3(seed0: int = 1000, n_streams: int = 128):
+    """BASELINE.json configs[2]: one sliding window per WebSocket stream, as the socket delivers it: int16 PCM, length of stream i =
+    min(96 000, 7 200 * (1 + (5 i mod 14))) samples (0.45 s .. 6 s), every 4th stream is a flush (gets 600 ms of silence appended and,
+    in the dual-model variant, runs on the full model; src/server.py:1327-1329, 1351).  Returns (list of int16 arrays, flush flags)."""
+    wins, flush = [], []
+    for i in range(n_streams):
+        n = min(96000, 7200 * (1 + (5 * i) % 14))
+        x = speech_like(n, seed0 + i)
+        wins.append((np.clip(x, -1.0, 1.0) * 32767.0).astype(np.int16))
+        flush.append(i % 4 == 3)
+    return wins, flush
+
+
+def workload_c4_lengths(total_seconds: int = 3600, seed: int = 1234):
+    """BASELINE.json configs[3]: segment lengths (samples) of one hour of audio cut into 1-30 s pieces (~230 segments)."""
+    rng = np.random.default_rng(seed)
+    lens, total, target = [], 0, total_seconds * SR
+    while total < target:
+        ln = min(int(round(rng.uniform(1.0, 30.0) / 0.01)) * 160, target - total)
+        lens.append(ln)
+        total += ln
+    return lens
+
+
+def workload_c4_clips(lens, indices, seed0: int = 2000):
+    """The segments `indices` of the hour.  Segment j is a rotation of one 30 s speech-like signal (generating 3600 s of fresh
+    signal would dominate the bench's start-up; the content does not change the timing)."""
+    base = speech_like(30 * SR, seed0)
+    return [np.roll(base, 997 * j)[: lens[j]].copy() for j in indices]
