@@ -147,6 +147,12 @@ QASR_API int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const 
 QASR_API int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                          int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream, uint64_t* ticket_out);
 QASR_API int qasr_wait(qasr_handle_t h, uint64_t ticket);
+/* qasr_submit_pcm_host for clips that are NOT contiguous in pcm_host (what an LPT-sharded pool member receives): clip i is
+ * pcm_host[clip_begin[i], clip_begin[i] + clip_len[i]) and its tokens are written at row out_row[i] of out_host (bf16
+ * [out_capacity_tokens, output_dim]); one copy per clip each way instead of one per batch.  Same ticket rules. */
+QASR_API int qasr_submit_clips_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_begin, const int64_t* clip_len,
+                                    const int64_t* out_row, int n_clips, void* out_host, int64_t out_capacity_tokens, int64_t* token_lens_out,
+                                    void* stream, uint64_t* ticket_out);
 
 /* Log-mel end to end with host buffers (float32 [128, sum T] out). */
 QASR_API int qasr_logmel_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, float* mel_out_host,
@@ -222,7 +228,16 @@ QASR_API size_t qasr_pool_workspace_bytes(qasr_pool_t p);
 QASR_API int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                               int64_t out_capacity_tokens, int64_t* token_lens_out, int32_t* clip_device_out, uint64_t* ticket_out);
 QASR_API int qasr_pool_collect(qasr_pool_t p, uint64_t ticket);
-/* The sharding rule of qasr_pool_submit on its own (pure host code, no GPU needed): clip_shard_out[i] = index (0 .. n_devices-1)
+/* How qasr_pool_submit cuts a batch.  CONTIGUOUS: at most N contiguous clip ranges of near-equal mel-frame
+ * count -- every shard is one copy each way, in place.  LPT: longest-processing-time-first by mel frames (sort descending, each clip to
+ * the least-loaded member) -- near-optimal balance when clips are few and unequal, at one copy per clip.  AUTO (default): LPT when the
+ * batch has fewer than four clips per member, else CONTIGUOUS.  The output is in clip order either way. */
+#define QASR_SHARD_AUTO 0
+#define QASR_SHARD_CONTIGUOUS 1
+#define QASR_SHARD_LPT 2
+QASR_API int qasr_pool_set_sharding(qasr_pool_t p, int mode);
+QASR_API int qasr_pool_plan_mode(const int64_t* clip_offsets, int n_clips, int n_devices, int mode, int32_t* clip_shard_out);
+/* The CONTIGUOUS sharding rule on its own (pure host code, no GPU needed): clip_shard_out[i] = index (0 .. n_devices-1)
  * of the pool member clip i would be sent to -- contiguous ranges of near-equal mel-frame count. */
 QASR_API int qasr_pool_plan(const int64_t* clip_offsets, int n_clips, int n_devices, int32_t* clip_shard_out);
 QASR_API void qasr_pool_destroy(qasr_pool_t p);

@@ -34,7 +34,9 @@ struct Batch {  // one qasr_pool_submit
 struct Shard {
   std::shared_ptr<Batch> batch;
   const float* pcm_host = nullptr;
-  std::vector<int64_t> offsets;   // this shard's clip offsets (absolute sample indices into pcm_host)
+  std::vector<int64_t> offsets;   // contiguous shard: its clip offsets (absolute sample indices into pcm_host)
+  // scattered shard (LPT): per clip its first sample, length and first output row (absolute, into the caller's buffers)
+  std::vector<int64_t> begin, len, out_row;
   void* out_host = nullptr;
   int64_t out_capacity_tokens = 0;
   uint64_t handle_ticket = 0;
@@ -61,6 +63,7 @@ struct qasr_pool_s {
   uint64_t next_ticket = 1;
   std::map<uint64_t, std::shared_ptr<Batch>> batches;
   int output_dim = 0;
+  int sharding = QASR_SHARD_AUTO;
 };
 
 namespace {
@@ -82,6 +85,28 @@ void partition_clips(const std::vector<int64_t>& frames, int g, std::vector<int>
     (*cut)[k] = std::max(i, (*cut)[k - 1]);
   }
 }
+
+// Longest-processing-time-first: clips by mel frames descending (ties: lower index first), each to the
+// least-loaded member (ties: lower member first).  Deterministic; shard[i] = member of clip i.
+void lpt_assign(const std::vector<int64_t>& frames, int g, std::vector<int>* shard) {
+  const int n = static_cast<int>(frames.size());
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return frames[a] > frames[b]; });
+  std::vector<int64_t> load(g, 0);
+  shard->assign(n, 0);
+  for (int i : order) {
+    int best = 0;
+    for (int k = 1; k < g; ++k)
+      if (load[k] < load[best]) best = k;
+    (*shard)[i] = best;
+    load[best] += frames[i];
+  }
+}
+
+// QASR_SHARD_AUTO: contiguous ranges (one copy each way per shard) unless the batch has fewer than four clips per member, where a
+// range boundary can cost a whole clip of imbalance and LPT's per-clip copies are few
+bool use_lpt(int mode, int n_clips, int g) { return mode == QASR_SHARD_LPT || (mode == QASR_SHARD_AUTO && g > 1 && n_clips < 4 * g); }
 
 void finish_shard(qasr_pool_s* p, Shard& s, int rc) {
   std::string err;
@@ -119,11 +144,14 @@ void worker_main(qasr_pool_s* p, Worker* w) {
       }
     }
     if (enqueue) {
-      const int n = static_cast<int>(s.offsets.size()) - 1;
       // token lengths were already reported by qasr_pool_submit itself: nothing the caller owns besides the PCM and output
       // buffers is touched from this thread
-      const int rc = qasr_submit_pcm_host(w->handle, s.pcm_host, s.offsets.data(), n, s.out_host, s.out_capacity_tokens, nullptr,
-                                          w->stream, &s.handle_ticket);
+      const int rc = s.begin.empty()
+                         ? qasr_submit_pcm_host(w->handle, s.pcm_host, s.offsets.data(), static_cast<int>(s.offsets.size()) - 1, s.out_host,
+                                                s.out_capacity_tokens, nullptr, w->stream, &s.handle_ticket)
+                         : qasr_submit_clips_host(w->handle, s.pcm_host, s.begin.data(), s.len.data(), s.out_row.data(),
+                                                  static_cast<int>(s.begin.size()), s.out_host, s.out_capacity_tokens, nullptr, w->stream,
+                                                  &s.handle_ticket);
       if (rc != 0) {
         finish_shard(p, s, rc);
       } else {
@@ -211,11 +239,31 @@ int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_o
   }
   QASR_REQUIRE(tok_off[n_clips] <= out_capacity_tokens, "qasr_pool_submit: output buffer too small for " + std::to_string(tok_off[n_clips]) + " tokens");
   const int g = static_cast<int>(p->workers.size());
-  std::vector<int> cut;
-  partition_clips(frames, g, &cut);
   auto batch = std::make_shared<Batch>();
   std::vector<std::pair<int, Shard>> shards;
-  for (int k = 0; k < g; ++k) {
+  if (use_lpt(p->sharding, n_clips, g)) {
+    std::vector<int> member;
+    lpt_assign(frames, g, &member);
+    std::vector<Shard> per(g);
+    for (int i = 0; i < n_clips; ++i) {
+      Shard& s = per[member[i]];
+      s.begin.push_back(clip_offsets[i]);
+      s.len.push_back(clip_offsets[i + 1] - clip_offsets[i]);
+      s.out_row.push_back(tok_off[i]);
+      if (clip_device_out != nullptr) clip_device_out[i] = p->workers[member[i]]->device;
+    }
+    for (int k = 0; k < g; ++k) {
+      if (per[k].begin.empty()) continue;
+      per[k].batch = batch;
+      per[k].pcm_host = pcm_host;
+      per[k].out_host = out_host;
+      per[k].out_capacity_tokens = out_capacity_tokens;
+      shards.emplace_back(k, std::move(per[k]));
+    }
+  }
+  std::vector<int> cut;
+  if (shards.empty()) partition_clips(frames, g, &cut);
+  for (int k = 0; k < g && !cut.empty(); ++k) {
     const int a = cut[k], b = cut[k + 1];
     if (clip_device_out != nullptr)
       for (int i = a; i < b; ++i) clip_device_out[i] = p->workers[k]->device;
@@ -240,18 +288,37 @@ int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_o
   return 0;
 }
 
-int qasr_pool_plan(const int64_t* clip_offsets, int n_clips, int n_devices, int32_t* clip_shard_out) {
+int qasr_pool_set_sharding(qasr_pool_t p, int mode) {
+  QASR_REQUIRE(p != nullptr, "qasr_pool_set_sharding: null pool");
+  QASR_REQUIRE(mode == QASR_SHARD_AUTO || mode == QASR_SHARD_CONTIGUOUS || mode == QASR_SHARD_LPT, "qasr_pool_set_sharding: unknown mode");
+  std::lock_guard<std::mutex> lk(p->mu);
+  p->sharding = mode;
+  return 0;
+}
+
+int qasr_pool_plan_mode(const int64_t* clip_offsets, int n_clips, int n_devices, int mode, int32_t* clip_shard_out) {
   QASR_REQUIRE(clip_offsets != nullptr && clip_shard_out != nullptr && n_clips >= 0 && n_devices >= 1, "qasr_pool_plan: bad argument");
+  QASR_REQUIRE(mode == QASR_SHARD_AUTO || mode == QASR_SHARD_CONTIGUOUS || mode == QASR_SHARD_LPT, "qasr_pool_plan: unknown mode");
   std::vector<int64_t> frames(n_clips);
   for (int i = 0; i < n_clips; ++i) {
     QASR_REQUIRE(clip_offsets[i + 1] >= clip_offsets[i], "qasr_pool_plan: offsets must be non-decreasing");
     frames[i] = (clip_offsets[i + 1] - clip_offsets[i]) / 160;
+  }
+  if (use_lpt(mode, n_clips, n_devices)) {
+    std::vector<int> member;
+    lpt_assign(frames, n_devices, &member);
+    for (int i = 0; i < n_clips; ++i) clip_shard_out[i] = member[i];
+    return 0;
   }
   std::vector<int> cut;
   partition_clips(frames, n_devices, &cut);
   for (int k = 0; k < n_devices; ++k)
     for (int i = cut[k]; i < cut[k + 1]; ++i) clip_shard_out[i] = k;
   return 0;
+}
+
+int qasr_pool_plan(const int64_t* clip_offsets, int n_clips, int n_devices, int32_t* clip_shard_out) {
+  return qasr_pool_plan_mode(clip_offsets, n_clips, n_devices, QASR_SHARD_CONTIGUOUS, clip_shard_out);
 }
 
 int qasr_pool_collect(qasr_pool_t p, uint64_t ticket) {

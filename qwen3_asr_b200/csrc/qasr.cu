@@ -846,7 +846,6 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
                 int64_t* feature_lens_out, void* stream_v) {
   QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_logmel: bad argument");
   if (n_clips == 0) return 0;
-  QASR_REQUIRE(pcm_dev != nullptr && mel_out_dev != nullptr, "qasr_logmel: null buffer");
   QASR_REQUIRE(n_clips <= 65535, "qasr_logmel: at most 65535 clips per call");
   DeviceGuard guard(h->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -866,7 +865,8 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
     n_items += static_cast<size_t>((t + mel::FB - 1) / mel::FB) + static_cast<size_t>((t + mel::CLAMP_TILE - 1) / mel::CLAMP_TILE);
   }
   QASR_REQUIRE(mel_ld >= cols, "qasr_logmel: mel_ld smaller than the total frame count");
-  if (cols == 0) return 0;
+  if (cols == 0) return 0;   // only empty clips: nothing to read or write (the buffers may be null)
+  QASR_REQUIRE(pcm_dev != nullptr && mel_out_dev != nullptr, "qasr_logmel: null buffer");
   if (stream_enter(h, stream) != 0) return 2;
 
   // Work list in ticket order: frame items clip by clip; the clamp items of a clip are emitted once kClampLag frame
@@ -1048,23 +1048,19 @@ int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_o
   return qasr_encode(h, mel, QASR_F32, ld, flens.data(), n_clips, out_dev, token_lens_out, stream);
 }
 
-int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
-                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream_v, uint64_t* ticket_out) {
-  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0 && ticket_out != nullptr, "qasr_submit_pcm_host: bad argument");
-  QASR_REQUIRE(h->finalized, "qasr_submit_pcm_host before qasr_finalize");
-  *ticket_out = 0;
-  if (n_clips == 0) return 0;
-  QASR_REQUIRE(pcm_host != nullptr && out_host != nullptr, "qasr_submit_pcm_host: null buffer");
+namespace {
+// One pipelined host -> device -> host pass.  Clip i is pcm_host[begin[i], begin[i] + len[i]); its tokens land at row out_row[i] of
+// out_host (out_row == nullptr: clips are contiguous in pcm_host and rows follow each other -- ONE copy each way).
+int submit_impl(qasr_handle_t h, const float* pcm_host, const int64_t* begin, const int64_t* len, const int64_t* out_row, int n_clips,
+                void* out_host, int64_t* token_lens_out, cudaStream_t stream, uint64_t* ticket_out) {
   DeviceGuard guard(h->device);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const int64_t base = clip_offsets[0];
-  const int64_t n_samples = clip_offsets[n_clips] - base;
-  long long tokens = 0;
-  std::vector<int64_t> offs(n_clips + 1);
-  for (int i = 0; i <= n_clips; ++i) offs[i] = clip_offsets[i] - base;
-  for (int i = 0; i < n_clips; ++i) tokens += qasr_token_len((offs[i + 1] - offs[i]) / mel::HOP);
-  QASR_REQUIRE(tokens <= out_capacity_tokens, "qasr_submit_pcm_host: output buffer too small for " + std::to_string(tokens) + " tokens");
-
+  std::vector<int64_t> offs(n_clips + 1, 0), tok_off(n_clips + 1, 0);
+  for (int i = 0; i < n_clips; ++i) {
+    offs[i + 1] = offs[i] + len[i];
+    tok_off[i + 1] = tok_off[i] + qasr_token_len(len[i] / mel::HOP);
+  }
+  const int64_t n_samples = offs[n_clips];
+  const long long tokens = tok_off[n_clips];
   if (h->s_in == nullptr) {
     QASR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     QASR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -1078,7 +1074,8 @@ int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* 
                                                       std::to_string(h->pipe[h->next_ticket & 1].seq) + " first");
   const uint64_t ticket = h->next_ticket++;
   qasr_handle_s::Pipe& pp = h->pipe[ticket & 1];
-  const size_t out_bytes = static_cast<size_t>(tokens) * h->cfg.output_dim * sizeof(bf16);
+  const size_t row_bytes = static_cast<size_t>(h->cfg.output_dim) * sizeof(bf16);
+  const size_t out_bytes = static_cast<size_t>(tokens) * row_bytes;
   if (grow(h, &pp.pcm, static_cast<size_t>(n_samples) * sizeof(float)) != 0) return 2;   // growing synchronises the device
   if (grow(h, &pp.out, out_bytes) != 0) return 2;
   // the slot's previous user (ticket - 2): its compute must have finished reading pp.pcm before the copy engine overwrites
@@ -1087,19 +1084,73 @@ int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* 
     QASR_CUDA_CHECK(cudaStreamWaitEvent(h->s_in, pp.ev_comp, 0));
     QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, pp.ev_out, 0));
   }
-  QASR_CUDA_CHECK(cudaMemcpyAsync(pp.pcm.p, pcm_host + base, static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+  float* dpcm = static_cast<float*>(pp.pcm.p);
+  if (out_row == nullptr) {
+    QASR_CUDA_CHECK(cudaMemcpyAsync(dpcm, pcm_host + begin[0], static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+  } else {
+    for (int i = 0; i < n_clips; ++i)
+      if (len[i] > 0)
+        QASR_CUDA_CHECK(cudaMemcpyAsync(dpcm + offs[i], pcm_host + begin[i], static_cast<size_t>(len[i]) * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+  }
   QASR_CUDA_CHECK(cudaEventRecord(pp.ev_in, h->s_in));
   QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, pp.ev_in, 0));
-  const int rc = qasr_encode_pcm(h, static_cast<const float*>(pp.pcm.p), offs.data(), n_clips, pp.out.p, token_lens_out, stream);
+  const int rc = qasr_encode_pcm(h, dpcm, offs.data(), n_clips, pp.out.p, token_lens_out, stream);
   if (rc != 0) return rc;
   QASR_CUDA_CHECK(cudaEventRecord(pp.ev_comp, stream));
   QASR_CUDA_CHECK(cudaStreamWaitEvent(h->s_out, pp.ev_comp, 0));
-  if (out_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(out_host, pp.out.p, out_bytes, cudaMemcpyDeviceToHost, h->s_out));
+  if (out_row == nullptr) {
+    if (out_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(out_host, pp.out.p, out_bytes, cudaMemcpyDeviceToHost, h->s_out));
+  } else {
+    for (int i = 0; i < n_clips; ++i) {
+      const size_t nb = static_cast<size_t>(tok_off[i + 1] - tok_off[i]) * row_bytes;
+      if (nb > 0)
+        QASR_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(out_host) + static_cast<size_t>(out_row[i]) * row_bytes,
+                                        static_cast<const char*>(pp.out.p) + static_cast<size_t>(tok_off[i]) * row_bytes, nb,
+                                        cudaMemcpyDeviceToHost, h->s_out));
+    }
+  }
   QASR_CUDA_CHECK(cudaEventRecord(pp.ev_out, h->s_out));
   pp.seq = ticket;
   pp.waited = false;
   *ticket_out = ticket;
   return 0;
+}
+}  // namespace
+
+int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
+                         int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream_v, uint64_t* ticket_out) {
+  QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0 && ticket_out != nullptr, "qasr_submit_pcm_host: bad argument");
+  QASR_REQUIRE(h->finalized, "qasr_submit_pcm_host before qasr_finalize");
+  *ticket_out = 0;
+  if (n_clips == 0) return 0;
+  QASR_REQUIRE(pcm_host != nullptr && out_host != nullptr, "qasr_submit_pcm_host: null buffer");
+  std::vector<int64_t> begin(n_clips), len(n_clips);
+  long long tokens = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    begin[i] = clip_offsets[i];
+    len[i] = clip_offsets[i + 1] - clip_offsets[i];
+    QASR_REQUIRE(len[i] >= 0, "qasr_submit_pcm_host: offsets must be non-decreasing");
+    tokens += qasr_token_len(len[i] / mel::HOP);
+  }
+  QASR_REQUIRE(tokens <= out_capacity_tokens, "qasr_submit_pcm_host: output buffer too small for " + std::to_string(tokens) + " tokens");
+  return submit_impl(h, pcm_host, begin.data(), len.data(), nullptr, n_clips, out_host, token_lens_out, static_cast<cudaStream_t>(stream_v), ticket_out);
+}
+
+int qasr_submit_clips_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_begin, const int64_t* clip_len, const int64_t* out_row,
+                           int n_clips, void* out_host, int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream_v,
+                           uint64_t* ticket_out) {
+  QASR_REQUIRE(h != nullptr && clip_begin != nullptr && clip_len != nullptr && out_row != nullptr && n_clips >= 0 && ticket_out != nullptr,
+               "qasr_submit_clips_host: bad argument");
+  QASR_REQUIRE(h->finalized, "qasr_submit_clips_host before qasr_finalize");
+  *ticket_out = 0;
+  if (n_clips == 0) return 0;
+  QASR_REQUIRE(pcm_host != nullptr && out_host != nullptr, "qasr_submit_clips_host: null buffer");
+  for (int i = 0; i < n_clips; ++i) {
+    QASR_REQUIRE(clip_begin[i] >= 0 && clip_len[i] >= 0 && out_row[i] >= 0, "qasr_submit_clips_host: negative offset");
+    QASR_REQUIRE(out_row[i] + qasr_token_len(clip_len[i] / mel::HOP) <= out_capacity_tokens,
+                 "qasr_submit_clips_host: clip " + std::to_string(i) + " would write past the output buffer");
+  }
+  return submit_impl(h, pcm_host, clip_begin, clip_len, out_row, n_clips, out_host, token_lens_out, static_cast<cudaStream_t>(stream_v), ticket_out);
 }
 
 int qasr_wait(qasr_handle_t h, uint64_t ticket) {

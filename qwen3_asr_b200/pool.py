@@ -21,7 +21,7 @@ from .encoder import _DTYPES, make_config, sinusoid_table
 
 class B200EncoderPool:
     def __init__(self, cfg, weights: Mapping[str, "torch.Tensor | np.ndarray"], devices: Sequence[int] | None = None,
-                 max_chunks: int = 0, max_tokens: int = 0, quantize: str | None = None):
+                 max_chunks: int = 0, max_tokens: int = 0, quantize: str | None = None, sharding: str = "auto"):
         if not torch.cuda.is_available():
             raise QasrError("B200EncoderPool needs CUDA devices; this backend has no CPU path")
         self.lib = load_library()
@@ -33,6 +33,10 @@ class B200EncoderPool:
         check(self.lib, self.lib.qasr_pool_create(C.byref(self.cfg), devs, len(self.devices), C.byref(h)), "qasr_pool_create")
         self._h = h
         try:
+            modes = {"auto": 0, "contiguous": 1, "lpt": 2}
+            if sharding not in modes:
+                raise QasrError(f"unknown sharding mode {sharding!r}; expected one of {sorted(modes)}")
+            check(self.lib, self.lib.qasr_pool_set_sharding(self._h, modes[sharding]), "qasr_pool_set_sharding")
             for name, w in weights.items():
                 if "positional_embedding" in name and name != "positional_embedding":
                     continue

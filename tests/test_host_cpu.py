@@ -181,3 +181,34 @@ def test_pool_sharding_rule_on_the_host(lib):
     s = plan([16000, 0, 16000, 16000], 2)
     assert np.all(np.diff(s) >= 0) and set(s.tolist()) == {0, 1}
     assert plan([], 3).tolist() == []
+
+
+def test_pool_lpt_rule_matches_the_survey_definition(lib):
+    """qasr_pool_plan_mode(LPT) = SURVEY 8(e): sort by mel frames descending, each clip to the least-loaded GPU -- the same rule as
+    synth.lpt_assign (which bench.py --config c4 shards by); AUTO switches to it below four clips per GPU."""
+    import ctypes as C
+
+    from qwen3_asr_b200.synth import lpt_assign, workload_c4_lengths
+
+    def plan(lens, g, mode):
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out = np.full(len(lens), -1, dtype=np.int32)
+        assert lib.qasr_pool_plan_mode(offs.ctypes.data_as(C.POINTER(C.c_int64)), len(lens), g, mode, out.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        return out
+
+    AUTO, CONTIG, LPT = 0, 1, 2
+    lens = workload_c4_lengths()
+    frames = [n // 160 for n in lens]
+    for g in (2, 4, 8):
+        s = plan(lens, g, LPT)
+        bins = lpt_assign(frames, g)
+        assert [sorted(np.where(s == k)[0].tolist()) for k in range(g)] == bins
+        load = np.array([sum(frames[i] for i in b) for b in bins])
+        assert load.max() / (sum(frames) / g) - 1.0 <= 0.02          # SURVEY 8(e): <= 2 % imbalance at 8 GPUs with ~230 segments
+        assert plan(lens, g, AUTO).tolist() == plan(lens, g, CONTIG).tolist()      # many clips per GPU: zero-copy contiguous ranges
+    # few, unequal clips: contiguous ranges cannot balance, LPT can
+    few = [30 * 16000, 29 * 16000, 2 * 16000, 2 * 16000, 1 * 16000]
+    c, l = plan(few, 2, CONTIG), plan(few, 2, LPT)
+    fr = np.array(few) // 160
+    worst = lambda s: max(fr[s == k].sum() for k in range(2))
+    assert worst(l) < worst(c) and plan(few, 2, AUTO).tolist() == l.tolist()
