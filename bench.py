@@ -424,6 +424,7 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        timed.host_ms = (time.time() - w0) * 1e3 / steps   # host time to ENQUEUE one step (what the calling thread is busy for)
         if after is not None:
             after()
         e1.record()
@@ -437,7 +438,9 @@ def main():
     torch.cuda.synchronize()
     l0 = sum(e.launch_count for e in encs)
     ms_dev, _, win_dev = timed(work.step_dev, args.steps)
+    host_ms_dev = timed.host_ms
     launches = sum(e.launch_count for e in encs) - l0
+    graph_stats = [e.graph_stats() for e in encs]
 
     # same K steps again with per-launch CUDA events on the launching stream -> per-kernel durations
     for e in encs:
@@ -536,6 +539,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": work.h2d, "d2h_bytes_per_step": work.d2h, "api": work.api},
             "gpu_launches": int(launches),
+            # time the calling thread spends enqueueing one step; with the graph cache a repeated shape is one cudaGraphLaunch
+            "host_enqueue_ms_per_step": host_ms_dev, "graph_cache": graph_stats,
             "clocks": clocks,
             "roofline": roofline, "roofline_mel": roofline_mel, "kernels": kernels,
             "ms_per_step_profiled": ms_prof / args.steps,

@@ -245,6 +245,12 @@ QASR_API void qasr_pool_destroy(qasr_pool_t p);
 /* ---- launch accounting and per-launch timing (measurement; bench.py's roofline figures) ------- */
 /* Number of CUDA kernels this handle has launched so far. */
 QASR_API uint64_t qasr_launch_count(qasr_handle_t h);
+/* Graph cache: qasr_encode / qasr_encode_pcm calls whose shape (entry point, dtype, every clip length) repeats are captured into a
+ * CUDA graph on the second sighting and replayed from then on (same kernels and arguments, entry-owned buffers: bit-identical
+ * results, one launch instead of ~130-180).  Calls of more than 128 one-second chunks run eagerly unless QASR_GRAPH=all;
+ * QASR_GRAPH=0 switches the cache off.  Number of live graphs, replays so far, device bytes they hold (counters the kernels
+ * launched by a replay are included in qasr_launch_count). */
+QASR_API int qasr_graph_stats(qasr_handle_t h, int* n_graphs, uint64_t* replays, size_t* bytes);
 /* on != 0: bracket every kernel launch with CUDA events on the launching stream (clears earlier
  * records).  qasr_profile_read synchronises the device and returns, aggregated by kernel name in
  * first-launch order: '\n'-separated names, summed milliseconds, summed algorithmic work (FLOPs;

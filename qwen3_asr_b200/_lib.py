@@ -72,6 +72,7 @@ SIGNATURES = {
     "qasr_pool_plan_mode": (C.c_int, [_I64P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "qasr_pool_destroy": (None, [_P]),
     "qasr_launch_count": (C.c_uint64, [_P]),
+    "qasr_graph_stats": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
     "qasr_profile_enable": (C.c_int, [_P, C.c_int]),
     "qasr_profile_read": (C.c_int, [_P, C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)]),

@@ -182,6 +182,17 @@ struct qasr_handle_s {
   cudaEvent_t ev_last = nullptr;
   cudaStream_t last_stream = nullptr;
   bool has_last = false;
+
+  // CUDA-graph replay of repeated call shapes (see "graph cache" below)
+  struct GraphEntry;
+  std::vector<GraphEntry*> graphs;
+  std::map<std::vector<int64_t>, int> graph_seen;   // key -> sightings before a graph is built for it
+  GraphEntry* capturing = nullptr;                  // non-null while a call is being captured into a graph
+  int graph_max_chunks = 128;                       // calls with more 1-s chunks run eagerly (QASR_GRAPH=all lifts the limit)
+  size_t graph_bytes = 0;
+  uint64_t graph_clock = 0;
+  cudaStream_t s_cap = nullptr;                     // captures run on this stream (the caller's may be the legacy default stream, which cannot capture)
+  unsigned long long graph_replays = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   uint64_t next_ticket = 1;
 
@@ -223,8 +234,59 @@ int grow(qasr_handle_s* h, GrowBuf* b, size_t bytes) {
   return 0;
 }
 
+}  // namespace
+
+// ---- graph cache ----------------------------------------------------------------------------------------------------------
+// A forward is a chain of ~130-180 dependent kernel launches; for the calls the reference actually makes -- one WS window or one
+// SSE chunk per job (src/server.py:79-94), i.e. a handful of distinct shapes over and over -- the launches cost the single infer
+// thread more time than the kernels need.  The second time a call shape (entry point, dtype, every clip length) is seen, the
+// whole call is captured into a CUDA graph whose nodes read and write ENTRY-OWNED buffers (input copy, log-mel, tables, output),
+// so a replay is: one device-to-device copy in, one cudaGraphLaunch, one copy out, whatever pointers the caller passes.  Same
+// kernels, same order, same arguments as the eager path: results are bit-identical (tests/test_gpu_graph.py).
+struct qasr_handle_s::GraphEntry {
+  std::vector<int64_t> key;
+  cudaGraphExec_t exec = nullptr;
+  void* in = nullptr;            // copy of the caller's input: packed PCM (float) or packed mel [128, in_ld]
+  void* out = nullptr;           // bf16 [tokens, output_dim]
+  float* mel = nullptr;          // PCM entry point: the log-mel between the two halves
+  unsigned int* counters = nullptr;
+  uint8_t *tab_host = nullptr, *tab_dev = nullptr;   // every table the call ships (mel work items, chunk / window plans), pinned
+  size_t tab_cap = 0, tab_used = 0;
+  size_t in_bytes = 0, out_bytes = 0, bytes = 0;
+  long long in_ld = 0;
+  std::vector<int64_t> token_lens;
+  unsigned long long kernel_launches = 0;
+  uint64_t last_use = 0;
+  Staging fake;                  // what staging_acquire hands out while capturing
+};
+
+namespace {
+
+void graph_entry_free(qasr_handle_s* h, qasr_handle_s::GraphEntry* e) {
+  if (e == nullptr) return;
+  if (e->exec != nullptr) cudaGraphExecDestroy(e->exec);
+  for (void* p : {e->in, e->out, static_cast<void*>(e->mel), static_cast<void*>(e->counters), static_cast<void*>(e->tab_dev)})
+    if (p != nullptr) cudaFree(p);
+  if (e->tab_host != nullptr) cudaFreeHost(e->tab_host);
+  h->graph_bytes -= std::min(h->graph_bytes, e->bytes);
+  delete e;
+}
+
 // Acquire a staging slot with at least `bytes` of pinned host + device memory.
 int staging_acquire(qasr_handle_s* h, size_t bytes, Staging** out) {
+  if (h->capturing != nullptr) {  // bump-allocate from the graph entry's own table block: it must outlive (and not change under) the graph
+    qasr_handle_s::GraphEntry* e = h->capturing;
+    const size_t at = align_up(e->tab_used, 256);
+    QASR_REQUIRE(at + bytes <= e->tab_cap, "graph capture: table block too small");
+    e->tab_used = at + bytes;
+    e->fake.host = e->tab_host + at;
+    e->fake.dev = e->tab_dev + at;
+    e->fake.cap = bytes;
+    e->fake.ev = nullptr;
+    e->fake.in_flight = false;
+    *out = &e->fake;
+    return 0;
+  }
   Staging* s = &h->staging[h->next_slot];
   h->next_slot = (h->next_slot + 1) % kStagingSlots;
   if (s->ev == nullptr) QASR_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
@@ -252,11 +314,13 @@ int staging_acquire(qasr_handle_s* h, size_t bytes, Staging** out) {
 }
 
 int stream_enter(qasr_handle_s* h, cudaStream_t stream) {
+  if (h->capturing != nullptr) return 0;   // the capture is bracketed by its caller
   if (h->ev_last == nullptr) QASR_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
   if (h->has_last && stream != h->last_stream) QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, h->ev_last, 0));
   return 0;
 }
 int stream_leave(qasr_handle_s* h, cudaStream_t stream) {
+  if (h->capturing != nullptr) return 0;
   QASR_CUDA_CHECK(cudaEventRecord(h->ev_last, stream));
   h->last_stream = stream;
   h->has_last = true;
@@ -564,8 +628,10 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   if ((rc = linear("proj1_gemm", 2.0 * ntok * d * d, &h->tm_h, ln_out, h->proj1, LIN_GELU, h->att, d, nullptr)) != 0) return rc;
   if ((rc = linear("proj2_gemm", 2.0 * ntok * d * c.output_dim, &h->tm_att, h->att, h->proj2, LIN_PLAIN, out, out_ld, nullptr, row_map)) != 0) return rc;
 
-  QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
-  st->in_flight = true;
+  if (h->capturing == nullptr) {
+    QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
+    st->in_flight = true;
+  }
   h->last_chunks = nc;
   h->last_tokens = ntok;
   return 0;
@@ -624,7 +690,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   const int v_att = env_choice("QASR_ATTENTION", {"tc", "mma_sync"});
   const int v_keep = env_choice("QASR_DEBUG_KEEP", {"0", "1"});
   const int v_pdl = env_choice("QASR_PDL", {"1", "0"});
-  const int v_graph = env_choice("QASR_GRAPH", {"1", "0"});
+  const int v_graph = env_choice("QASR_GRAPH", {"1", "0", "all"});
   if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0) {
     delete h;
     return 1;
@@ -642,7 +708,8 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->ln_epi_stats = h->ln_fold && cfg->d_model % 64 == 0 && v_ln == 2;
   h->attn_simt = v_att == 1;
   h->keep_debug = v_keep == 1;
-  h->use_graph = v_graph == 0;
+  h->use_graph = v_graph != 1;
+  if (v_graph == 2) h->graph_max_chunks = 1 << 30;   // QASR_GRAPH=all: also replay large batches (the one-process pool: 8 x 176 launches per step)
 
   mel::Tables* host_tables = new mel::Tables();
   int rc = 0;
@@ -912,13 +979,19 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   }
   while (pend_head < pending.size()) emit_clamps(pending[pend_head++]);
   QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
-  if (grow(h, &h->clipmax_buf, (2 * static_cast<size_t>(n_clips) + 1) * sizeof(unsigned int)) != 0) return 2;
+  unsigned int* counters = h->capturing != nullptr ? h->capturing->counters : nullptr;
+  if (counters == nullptr) {
+    if (grow(h, &h->clipmax_buf, (2 * static_cast<size_t>(n_clips) + 1) * sizeof(unsigned int)) != 0) return 2;
+    counters = static_cast<unsigned int*>(h->clipmax_buf.p);
+  }
   const double mel_bytes = 4.0 * static_cast<double>(clip_offsets[n_clips] - clip_offsets[0]) + 4.0 * mel::N_MELS * static_cast<double>(cols);
   QASR_LAUNCH(h, "logmel", mel_bytes, stream,
               launch_logmel(pcm_dev, reinterpret_cast<const mel::Item*>(st->dev), static_cast<int>(ni), h->mel_tables, mel_out_dev, mel_ld,
-                            static_cast<unsigned int*>(h->clipmax_buf.p), n_clips, h->num_sms, stream));
-  QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
-  st->in_flight = true;
+                            counters, n_clips, h->num_sms, stream));
+  if (h->capturing == nullptr) {
+    QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
+    st->in_flight = true;
+  }
   h->last_mel_cols = cols;
   h->last_mel_ld = mel_ld;
   return stream_leave(h, stream);
@@ -929,8 +1002,144 @@ int encode_impl(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel
                 int64_t out_ld, const int64_t* token_rows_dev, int64_t* token_lens_out, void* stream_v);
 }
 
+namespace {
+enum GraphKind : int { GK_ENCODE = 1, GK_ENCODE_PCM = 2 };
+constexpr size_t kGraphBytesCap = 1ull << 30;
+constexpr size_t kGraphMaxEntries = 64;
+
+// Replay (or, on the second sighting of a call shape, capture) one qasr_encode / qasr_encode_pcm call.  `lens`: feature lengths
+// (GK_ENCODE) or clip lengths in samples (GK_ENCODE_PCM); the input starts at in_dev (GK_ENCODE: column 0 of the packed mel).
+// Returns -1 when the call is to run eagerly, 0 when it was served by a graph, > 0 on error.
+int graph_dispatch(qasr_handle_t h, int kind, const void* in_dev, int mel_dtype, int64_t mel_ld, const int64_t* lens, int n_clips, void* out_dev,
+                   int64_t* token_lens_out, cudaStream_t stream) {
+  if (!h->use_graph || h->profiling || h->capturing != nullptr || h->keep_debug || n_clips <= 0 || in_dev == nullptr || out_dev == nullptr) return -1;
+  long long chunks = 0, cols = 0, samples = 0, tokens = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    if (lens[i] < 0) return -1;
+    if (kind == GK_ENCODE_PCM && lens[i] != 0 && lens[i] <= mel::N_FFT / 2) return -1;   // the eager path reports the error
+    const long long t = kind == GK_ENCODE_PCM ? lens[i] / mel::HOP : lens[i];
+    if (t >= (1LL << 30)) return -1;
+    cols += t;
+    samples += kind == GK_ENCODE_PCM ? lens[i] : 0;
+    chunks += (t + 99) / 100;
+    tokens += qasr_token_len(t);
+  }
+  if (tokens == 0 || chunks > h->graph_max_chunks) return -1;
+  if (kind == GK_ENCODE && mel_ld < cols) return -1;
+  std::vector<int64_t> key;
+  key.reserve(n_clips + 2);
+  key.push_back(kind);
+  key.push_back(mel_dtype);
+  key.insert(key.end(), lens, lens + n_clips);
+
+  qasr_handle_s::GraphEntry* e = nullptr;
+  for (auto* g : h->graphs)
+    if (g->key == key) { e = g; break; }
+  const size_t elt = kind == GK_ENCODE_PCM ? sizeof(float) : (mel_dtype == QASR_BF16 ? 2 : 4);
+  DeviceGuard guard(h->device);
+  if (e == nullptr) {
+    if (h->graph_seen.size() > 4096) h->graph_seen.clear();
+    int& seen = h->graph_seen[key];
+    if (seen < 0 || ++seen < 2) return -1;   // first sighting (or a shape whose capture failed): eager
+    // ---- build
+    e = new qasr_handle_s::GraphEntry();
+    e->key = key;
+    e->in_ld = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(cols, 1)), 8));
+    e->in_bytes = kind == GK_ENCODE_PCM ? static_cast<size_t>(samples) * sizeof(float) : static_cast<size_t>(e->in_ld) * mel::N_MELS * elt;
+    e->out_bytes = static_cast<size_t>(tokens) * h->cfg.output_dim * sizeof(bf16);
+    const size_t mel_bytes = kind == GK_ENCODE_PCM ? static_cast<size_t>(e->in_ld) * mel::N_MELS * sizeof(float) : 0;
+    const size_t cnt_bytes = (2 * static_cast<size_t>(n_clips) + 1) * sizeof(unsigned int);
+    e->tab_cap = (256u << 10) + 256 * static_cast<size_t>(chunks) + 64 * (static_cast<size_t>(cols) / 16 + 16 * static_cast<size_t>(n_clips));
+    e->bytes = e->in_bytes + e->out_bytes + mel_bytes + cnt_bytes + e->tab_cap;
+    while (!h->graphs.empty() && (h->graphs.size() >= kGraphMaxEntries || h->graph_bytes + e->bytes > kGraphBytesCap)) {
+      size_t lru = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i]->last_use < h->graphs[lru]->last_use) lru = i;
+      cudaDeviceSynchronize();   // the evicted graph may still be running
+      graph_entry_free(h, h->graphs[lru]);
+      h->graphs.erase(h->graphs.begin() + lru);
+    }
+    bool ok = e->bytes <= kGraphBytesCap;
+    ok = ok && cudaMalloc(&e->in, std::max<size_t>(e->in_bytes, 256)) == cudaSuccess;
+    ok = ok && cudaMalloc(&e->out, std::max<size_t>(e->out_bytes, 256)) == cudaSuccess;
+    ok = ok && (mel_bytes == 0 || cudaMalloc(reinterpret_cast<void**>(&e->mel), mel_bytes) == cudaSuccess);
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&e->counters), cnt_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&e->tab_dev), e->tab_cap) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&e->tab_host), e->tab_cap) == cudaSuccess;
+    int rc = 0;
+    cudaGraph_t graph = nullptr;
+    if (ok) {
+      h->graph_bytes += e->bytes;
+      e->token_lens.assign(n_clips, 0);
+      const unsigned long long l0 = h->launches;
+      const char* why = "cudaStreamBeginCapture";
+      cudaStream_t caller_stream = stream;
+      if (h->s_cap == nullptr) ok = cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking) == cudaSuccess;
+      stream = h->s_cap;
+      ok = ok && cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      if (ok) {
+        h->capturing = e;
+        if (kind == GK_ENCODE_PCM) {
+          std::vector<int64_t> offs(n_clips + 1, 0), flens(n_clips, 0);
+          for (int i = 0; i < n_clips; ++i) offs[i + 1] = offs[i] + lens[i];
+          rc = qasr_logmel(h, static_cast<const float*>(e->in), offs.data(), n_clips, e->mel, e->in_ld, flens.data(), stream);
+          if (rc == 0) rc = qasr_encode(h, e->mel, QASR_F32, e->in_ld, flens.data(), n_clips, e->out, e->token_lens.data(), stream);
+        } else {
+          rc = qasr_encode(h, e->in, mel_dtype, e->in_ld, lens, n_clips, e->out, e->token_lens.data(), stream);
+        }
+        h->capturing = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+        ok = rc == 0 && ce == cudaSuccess && graph != nullptr;
+        why = rc != 0 ? "the captured call failed" : "cudaStreamEndCapture";
+        if (ok) {
+          ok = cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess;
+          why = "cudaGraphInstantiate";
+        }
+        if (graph != nullptr) cudaGraphDestroy(graph);
+      }
+      if (!ok) {
+        const std::string inner = rc != 0 ? std::string(qasr_last_error()) : std::string(cudaGetErrorString(cudaPeekAtLastError()));
+        set_last_error(std::string("graph capture skipped (") + why + "): " + inner);
+      }
+      stream = caller_stream;
+      e->kernel_launches = h->launches - l0;
+      h->launches = l0;
+    } else {
+      h->graph_bytes += e->bytes;   // graph_entry_free subtracts it again
+    }
+    if (!ok) {
+      cudaGetLastError();           // clear a sticky-free launch / capture error; the call still runs eagerly
+      graph_entry_free(h, e);
+      seen = -1;                    // do not try this shape again
+      return -1;
+    }
+    h->graphs.push_back(e);
+  }
+  // ---- replay
+  if (stream_enter(h, stream) != 0) return 2;
+  if (kind == GK_ENCODE_PCM) {
+    if (e->in_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(e->in, in_dev, e->in_bytes, cudaMemcpyDeviceToDevice, stream));
+  } else if (cols > 0) {
+    QASR_CUDA_CHECK(cudaMemcpy2DAsync(e->in, static_cast<size_t>(e->in_ld) * elt, in_dev, static_cast<size_t>(mel_ld) * elt,
+                                      static_cast<size_t>(cols) * elt, mel::N_MELS, cudaMemcpyDeviceToDevice, stream));
+  }
+  QASR_CUDA_CHECK(cudaGraphLaunch(e->exec, stream));
+  QASR_CUDA_CHECK(cudaMemcpyAsync(out_dev, e->out, e->out_bytes, cudaMemcpyDeviceToDevice, stream));
+  if (token_lens_out != nullptr) std::memcpy(token_lens_out, e->token_lens.data(), sizeof(int64_t) * n_clips);
+  h->launches += e->kernel_launches;
+  ++h->graph_replays;
+  e->last_use = ++h->graph_clock;
+  h->last_tokens = static_cast<int>(tokens);
+  return stream_leave(h, stream);
+}
+}  // namespace
+
 int qasr_encode(qasr_handle_t h, const void* mel_dev, int mel_dtype, int64_t mel_ld, const int64_t* feature_lens, int n_clips,
                 void* out_dev, int64_t* token_lens_out, void* stream_v) {
+  if (h != nullptr && h->finalized && feature_lens != nullptr && (mel_dtype == QASR_F32 || mel_dtype == QASR_BF16)) {
+    const int g = graph_dispatch(h, GK_ENCODE, mel_dev, mel_dtype, mel_ld, feature_lens, n_clips, out_dev, token_lens_out, static_cast<cudaStream_t>(stream_v));
+    if (g >= 0) return g;
+  }
   return encode_impl(h, mel_dev, mel_dtype, mel_ld, feature_lens, n_clips, out_dev, h != nullptr ? h->cfg.output_dim : 0, nullptr, token_lens_out,
                      stream_v);
 }
@@ -1037,6 +1246,13 @@ int qasr_encode_pcm(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_o
   QASR_REQUIRE(h->finalized, "qasr_encode_pcm before qasr_finalize");
   if (n_clips == 0) return 0;
   DeviceGuard guard(h->device);
+  {
+    std::vector<int64_t> lens(n_clips);
+    for (int i = 0; i < n_clips; ++i) lens[i] = clip_offsets[i + 1] - clip_offsets[i];
+    const int g = graph_dispatch(h, GK_ENCODE_PCM, pcm_dev != nullptr ? pcm_dev + clip_offsets[0] : nullptr, QASR_F32, 0, lens.data(), n_clips, out_dev,
+                                 token_lens_out, static_cast<cudaStream_t>(stream));
+    if (g >= 0) return g;
+  }
   std::vector<int64_t> flens(n_clips);
   long long cols = 0;
   for (int i = 0; i < n_clips; ++i) cols += (clip_offsets[i + 1] - clip_offsets[i]) / mel::HOP;
@@ -1426,6 +1642,9 @@ void qasr_destroy(qasr_handle_t h) {
   for (auto& pp : h->pipe)
     for (cudaEvent_t e : {pp.ev_in, pp.ev_comp, pp.ev_out})
       if (e != nullptr) cudaEventDestroy(e);
+  for (auto* g : h->graphs) graph_entry_free(h, g);
+  h->graphs.clear();
+  if (h->s_cap != nullptr) cudaStreamDestroy(h->s_cap);
   if (h->ev_last != nullptr) cudaEventDestroy(h->ev_last);
   if (h->s_in != nullptr) cudaStreamDestroy(h->s_in);
   if (h->s_out != nullptr) cudaStreamDestroy(h->s_out);
@@ -1434,6 +1653,14 @@ void qasr_destroy(qasr_handle_t h) {
 
 // ---- launch accounting / per-launch timing ------------------------------------------------------
 uint64_t qasr_launch_count(qasr_handle_t h) { return h == nullptr ? 0 : h->launches; }
+
+int qasr_graph_stats(qasr_handle_t h, int* n_graphs, uint64_t* replays, size_t* bytes) {
+  QASR_REQUIRE(h != nullptr, "qasr_graph_stats: null handle");
+  if (n_graphs != nullptr) *n_graphs = static_cast<int>(h->graphs.size());
+  if (replays != nullptr) *replays = h->graph_replays;
+  if (bytes != nullptr) *bytes = h->graph_bytes;
+  return 0;
+}
 
 int qasr_profile_enable(qasr_handle_t h, int on) {
   QASR_REQUIRE(h != nullptr, "qasr_profile_enable: null handle");

@@ -314,6 +314,12 @@ class B200AudioEncoder:
     def launch_count(self) -> int:
         return int(self.lib.qasr_launch_count(self._h))
 
+    def graph_stats(self) -> dict:
+        """{"graphs": live CUDA graphs of repeated call shapes, "replays": calls served by one, "bytes": device bytes they hold}"""
+        n, r, b = C.c_int(0), C.c_uint64(0), C.c_size_t(0)
+        check(self.lib, self.lib.qasr_graph_stats(self._h, C.byref(n), C.byref(r), C.byref(b)), "qasr_graph_stats")
+        return {"graphs": int(n.value), "replays": int(r.value), "bytes": int(b.value)}
+
     def profile(self, on: bool = True) -> None:
         """Bracket every kernel launch with CUDA events on the launching stream (clears old records)."""
         check(self.lib, self.lib.qasr_profile_enable(self._h, 1 if on else 0), "qasr_profile_enable")
