@@ -147,6 +147,9 @@ QASR_API int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const 
 QASR_API int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                          int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream, uint64_t* ticket_out);
 QASR_API int qasr_wait(qasr_handle_t h, uint64_t ticket);
+/* Device-side durations of the three legs of a finished ticket (CUDA events on the copy-in, compute and copy-out streams): host->device
+ * copy, log-mel + encoder, device->host copy.  Valid after qasr_wait(ticket) until the same slot's next submit (ticket + 2). */
+QASR_API int qasr_pipe_times(qasr_handle_t h, uint64_t ticket, float* h2d_ms, float* compute_ms, float* d2h_ms);
 /* qasr_submit_pcm_host for clips that are NOT contiguous in pcm_host (what an LPT-sharded pool member receives): clip i is
  * pcm_host[clip_begin[i], clip_begin[i] + clip_len[i]) and its tokens are written at row out_row[i] of out_host (bf16
  * [out_capacity_tokens, output_dim]); one copy per clip each way instead of one per batch.  Same ticket rules. */
@@ -228,6 +231,11 @@ QASR_API size_t qasr_pool_workspace_bytes(qasr_pool_t p);
 QASR_API int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                               int64_t out_capacity_tokens, int64_t* token_lens_out, int32_t* clip_device_out, uint64_t* ticket_out);
 QASR_API int qasr_pool_collect(qasr_pool_t p, uint64_t ticket);
+/* Per-member averages since creation (or the last call with reset != 0), QASR_POOL_STAT_FIELDS doubles per member:
+ * shards, host ms spent enqueueing a shard, host ms blocked waiting for one, device ms of its host->device copy, of its compute, of
+ * its device->host copy, host ms from enqueue start to completion.  Tells a launch-bound pool from a copy-bound one. */
+#define QASR_POOL_STAT_FIELDS 7
+QASR_API int qasr_pool_stats(qasr_pool_t p, double* out, int capacity_members, int reset);
 /* How qasr_pool_submit cuts a batch.  CONTIGUOUS: at most N contiguous clip ranges of near-equal mel-frame
  * count -- every shard is one copy each way, in place.  LPT: longest-processing-time-first by mel frames (sort descending, each clip to
  * the least-loaded member) -- near-optimal balance when clips are few and unequal, at one copy per clip.  AUTO (default): LPT when the

@@ -49,6 +49,7 @@ SIGNATURES = {
     "qasr_encode_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P]),
     "qasr_submit_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P, C.POINTER(C.c_uint64)]),
     "qasr_wait": (C.c_int, [_P, C.c_uint64]),
+    "qasr_pipe_times": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "qasr_submit_clips_host": (C.c_int, [_P, _P, _I64P, _I64P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P, C.POINTER(C.c_uint64)]),
     "qasr_logmel_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, _I64P, _P]),
     "qasr_resample_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "qasr_pool_submit": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "qasr_pool_collect": (C.c_int, [_P, C.c_uint64]),
     "qasr_pool_plan": (C.c_int, [_I64P, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
+    "qasr_pool_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int, C.c_int]),
     "qasr_pool_set_sharding": (C.c_int, [_P, C.c_int]),
     "qasr_pool_plan_mode": (C.c_int, [_I64P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "qasr_pool_destroy": (None, [_P]),

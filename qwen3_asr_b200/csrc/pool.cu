@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -40,6 +41,11 @@ struct Shard {
   void* out_host = nullptr;
   int64_t out_capacity_tokens = 0;
   uint64_t handle_ticket = 0;
+  double t_enqueue0 = 0.0;        // host clock when the worker started enqueueing it
+};
+
+struct WorkerStats {
+  double shards = 0, enqueue_ms = 0, wait_ms = 0, h2d_ms = 0, compute_ms = 0, d2h_ms = 0, turnaround_ms = 0;
 };
 
 struct Worker {
@@ -49,6 +55,7 @@ struct Worker {
   std::thread thread;
   std::deque<Shard> queue;      // submitted, not yet enqueued on the GPU
   std::deque<Shard> inflight;   // enqueued (at most two: the handle double-buffers)
+  WorkerStats stats;            // guarded by the pool mutex
 };
 
 }  // namespace
@@ -122,6 +129,8 @@ void finish_shard(qasr_pool_s* p, Shard& s, int rc) {
   if (--s.batch->pending == 0) p->cv_done.notify_all();
 }
 
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 void worker_main(qasr_pool_s* p, Worker* w) {
   cudaSetDevice(w->device);
   for (;;) {
@@ -144,6 +153,7 @@ void worker_main(qasr_pool_s* p, Worker* w) {
       }
     }
     if (enqueue) {
+      s.t_enqueue0 = now_ms();
       // token lengths were already reported by qasr_pool_submit itself: nothing the caller owns besides the PCM and output
       // buffers is touched from this thread
       const int rc = s.begin.empty()
@@ -156,10 +166,22 @@ void worker_main(qasr_pool_s* p, Worker* w) {
         finish_shard(p, s, rc);
       } else {
         std::lock_guard<std::mutex> lk(p->mu);
+        w->stats.enqueue_ms += now_ms() - s.t_enqueue0;
         w->inflight.push_back(std::move(s));
       }
     } else {
+      const double t0 = now_ms();
       const int rc = qasr_wait(w->handle, s.handle_ticket);
+      const double t1 = now_ms();
+      float a = 0.f, b = 0.f, c = 0.f;
+      const bool timed = rc == 0 && qasr_pipe_times(w->handle, s.handle_ticket, &a, &b, &c) == 0;
+      {
+        std::lock_guard<std::mutex> lk(p->mu);
+        w->stats.shards += 1;
+        w->stats.wait_ms += t1 - t0;
+        w->stats.turnaround_ms += t1 - s.t_enqueue0;
+        if (timed) { w->stats.h2d_ms += a; w->stats.compute_ms += b; w->stats.d2h_ms += c; }
+      }
       finish_shard(p, s, rc);
     }
   }
@@ -336,6 +358,20 @@ int qasr_pool_collect(qasr_pool_t p, uint64_t ticket) {
   if (b->rc != 0) {
     qasr::set_last_error("qasr_pool_collect: a shard failed: " + b->error);
     return b->rc;
+  }
+  return 0;
+}
+
+int qasr_pool_stats(qasr_pool_t p, double* out, int capacity_members, int reset) {
+  QASR_REQUIRE(p != nullptr && out != nullptr && capacity_members >= static_cast<int>(p->workers.size()), "qasr_pool_stats: bad argument");
+  std::lock_guard<std::mutex> lk(p->mu);
+  for (size_t i = 0; i < p->workers.size(); ++i) {
+    WorkerStats& st = p->workers[i]->stats;
+    const double n = st.shards > 0 ? st.shards : 1.0;
+    double* o = out + i * QASR_POOL_STAT_FIELDS;
+    o[0] = st.shards; o[1] = st.enqueue_ms / n; o[2] = st.wait_ms / n; o[3] = st.h2d_ms / n; o[4] = st.compute_ms / n; o[5] = st.d2h_ms / n;
+    o[6] = st.turnaround_ms / n;
+    if (reset != 0) st = WorkerStats();
   }
   return 0;
 }

@@ -173,6 +173,7 @@ struct qasr_handle_s {
   struct Pipe {
     GrowBuf pcm, out;
     cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_h2d0 = nullptr, ev_comp0 = nullptr, ev_d2h0 = nullptr;   // starts of the three legs (qasr_pipe_times)
     uint64_t seq = 0;  // ticket of the submit that last used this slot (0 = never)
     bool waited = true;  // qasr_wait has been called for `seq`
   } pipe[2];
@@ -1281,9 +1282,7 @@ int submit_impl(qasr_handle_t h, const float* pcm_host, const int64_t* begin, co
     QASR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     QASR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     for (auto& pp : h->pipe) {
-      QASR_CUDA_CHECK(cudaEventCreateWithFlags(&pp.ev_in, cudaEventDisableTiming));
-      QASR_CUDA_CHECK(cudaEventCreateWithFlags(&pp.ev_comp, cudaEventDisableTiming));
-      QASR_CUDA_CHECK(cudaEventCreateWithFlags(&pp.ev_out, cudaEventDisableTiming));
+      for (cudaEvent_t* ev : {&pp.ev_in, &pp.ev_comp, &pp.ev_out, &pp.ev_h2d0, &pp.ev_comp0, &pp.ev_d2h0}) QASR_CUDA_CHECK(cudaEventCreate(ev));
     }
   }
   QASR_REQUIRE(h->pipe[h->next_ticket & 1].waited, "qasr_submit_pcm_host: two submits are already un-waited; call qasr_wait on ticket " +
@@ -1301,6 +1300,7 @@ int submit_impl(qasr_handle_t h, const float* pcm_host, const int64_t* begin, co
     QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, pp.ev_out, 0));
   }
   float* dpcm = static_cast<float*>(pp.pcm.p);
+  QASR_CUDA_CHECK(cudaEventRecord(pp.ev_h2d0, h->s_in));
   if (out_row == nullptr) {
     QASR_CUDA_CHECK(cudaMemcpyAsync(dpcm, pcm_host + begin[0], static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
   } else {
@@ -1310,10 +1310,12 @@ int submit_impl(qasr_handle_t h, const float* pcm_host, const int64_t* begin, co
   }
   QASR_CUDA_CHECK(cudaEventRecord(pp.ev_in, h->s_in));
   QASR_CUDA_CHECK(cudaStreamWaitEvent(stream, pp.ev_in, 0));
+  QASR_CUDA_CHECK(cudaEventRecord(pp.ev_comp0, stream));
   const int rc = qasr_encode_pcm(h, dpcm, offs.data(), n_clips, pp.out.p, token_lens_out, stream);
   if (rc != 0) return rc;
   QASR_CUDA_CHECK(cudaEventRecord(pp.ev_comp, stream));
   QASR_CUDA_CHECK(cudaStreamWaitEvent(h->s_out, pp.ev_comp, 0));
+  QASR_CUDA_CHECK(cudaEventRecord(pp.ev_d2h0, h->s_out));
   if (out_row == nullptr) {
     if (out_bytes > 0) QASR_CUDA_CHECK(cudaMemcpyAsync(out_host, pp.out.p, out_bytes, cudaMemcpyDeviceToHost, h->s_out));
   } else {
@@ -1378,6 +1380,21 @@ int qasr_wait(qasr_handle_t h, uint64_t ticket) {
   // a later submit on the same slot waited for this ticket's copies on the device; its own event then covers both
   if (pp.seq != 0) QASR_CUDA_CHECK(cudaEventSynchronize(pp.ev_out));
   if (pp.seq == ticket) pp.waited = true;
+  return 0;
+}
+
+int qasr_pipe_times(qasr_handle_t h, uint64_t ticket, float* h2d_ms, float* compute_ms, float* d2h_ms) {
+  QASR_REQUIRE(h != nullptr && ticket != 0 && ticket < h->next_ticket, "qasr_pipe_times: unknown ticket");
+  DeviceGuard guard(h->device);
+  qasr_handle_s::Pipe& pp = h->pipe[ticket & 1];
+  QASR_REQUIRE(pp.seq == ticket && pp.waited, "qasr_pipe_times: call it after qasr_wait(ticket) and before the slot's next submit");
+  float a = 0.f, b = 0.f, c = 0.f;
+  QASR_CUDA_CHECK(cudaEventElapsedTime(&a, pp.ev_h2d0, pp.ev_in));
+  QASR_CUDA_CHECK(cudaEventElapsedTime(&b, pp.ev_comp0, pp.ev_comp));
+  QASR_CUDA_CHECK(cudaEventElapsedTime(&c, pp.ev_d2h0, pp.ev_out));
+  if (h2d_ms != nullptr) *h2d_ms = a;
+  if (compute_ms != nullptr) *compute_ms = b;
+  if (d2h_ms != nullptr) *d2h_ms = c;
   return 0;
 }
 
@@ -1640,7 +1657,7 @@ void qasr_destroy(qasr_handle_t h) {
   for (GrowBuf* b : {&h->mel_buf, &h->pcm_buf, &h->out_buf, &h->clipmax_buf, &h->pipe[0].pcm, &h->pipe[0].out, &h->pipe[1].pcm, &h->pipe[1].out})
     if (b->p != nullptr) cudaFree(b->p);
   for (auto& pp : h->pipe)
-    for (cudaEvent_t e : {pp.ev_in, pp.ev_comp, pp.ev_out})
+    for (cudaEvent_t e : {pp.ev_in, pp.ev_comp, pp.ev_out, pp.ev_h2d0, pp.ev_comp0, pp.ev_d2h0})
       if (e != nullptr) cudaEventDestroy(e);
   for (auto* g : h->graphs) graph_entry_free(h, g);
   h->graphs.clear();

@@ -92,6 +92,14 @@ class B200EncoderPool:
               "qasr_pool_submit")
         return int(ticket.value), toks, devs
 
+    def stats(self, reset: bool = False) -> list:
+        """Per-member averages: where a shard's time goes (host enqueue / host wait / device H2D, compute, D2H / turnaround), ms."""
+        n = len(self)
+        buf = (C.c_double * (7 * n))()
+        check(self.lib, self.lib.qasr_pool_stats(self._h, buf, n, 1 if reset else 0), "qasr_pool_stats")
+        names = ("shards", "enqueue_ms", "wait_ms", "h2d_ms", "compute_ms", "d2h_ms", "turnaround_ms")
+        return [{"device": self.devices[i], **{k: round(buf[7 * i + j], 4) for j, k in enumerate(names)}} for i in range(n)]
+
     def collect(self, ticket: int) -> None:
         check(self.lib, self.lib.qasr_pool_collect(self._h, C.c_uint64(int(ticket))), "qasr_pool_collect")
 

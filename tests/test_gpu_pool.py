@@ -46,7 +46,7 @@ def test_pool_matches_single_handle_bitwise(tiny_cfg, n_handles):
     want = want.cpu()
     enc.close()
 
-    pool = B200EncoderPool(cfg, w, devices=devices, max_chunks=64)
+    pool = B200EncoderPool(cfg, w, devices=devices, max_chunks=64, sharding="contiguous")
     assert len(pool) == n_handles
     pcm, offs = _pack(clips)
     out = torch.zeros((int(want_toks.sum()), pool.output_dim), dtype=torch.bfloat16, pin_memory=True)
