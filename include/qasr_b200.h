@@ -196,6 +196,20 @@ QASR_API int qasr_resample_f32(qasr_handle_t h, const float* pcm_dev, const int6
  * (may be NULL to query the sizes); *width = the zero padding torchaudio applies on the left. */
 QASR_API int qasr_resample_f32_taps(int orig_sr, int new_sr, float* taps_out, int64_t capacity, int* n_phases, int* n_taps, int* width);
 
+/* Long-audio splitter: the SDK cuts audio longer than max_chunk_sec (1200 s) into chunks at low-energy points
+ * before encoding them as independent clips -- split_audio_into_chunks, which the reference relies on (LEARNING_LOG.md:215-219:
+ * "sliding window convolution with +/-5s search range"; src/server.py:867 enters it through model.transcribe).  For every cut wanted
+ * at start + max_chunk_sec * sr: inside [cut - expand, cut + expand) find the min_window_ms window with the smallest sum of |x|
+ * and cut at its quietest sample (first one on ties).  Arithmetic is exact (|x| quantised to floor(|x| * 2^40), int64 sums), so the
+ * boundaries are defined bit for bit.  The SDK's source is not available offline: PARITY UNPINNED against it, pinned against
+ * oracle/prefrontend.py::split_points, which restates the description above.  Synchronises `stream` (every cut depends on the last).
+ *   pcm_dev            mono float32 on the device, n_samples long
+ *   boundaries_out     host int64 [capacity]: 0 = b_0 < b_1 < ... < b_n = n_samples; chunk i is [b_i, b_i+1) -- directly usable as
+ *                      the clip_offsets of qasr_encode_pcm / qasr_pool_submit;  *n_chunks_out = n */
+QASR_API int qasr_split_audio(qasr_handle_t h, const float* pcm_dev, int64_t n_samples, int sample_rate, double max_chunk_sec,
+                              double search_expand_sec, double min_window_ms, int64_t* boundaries_out, int capacity, int* n_chunks_out,
+                              void* stream);
+
 /* One WS window per stream: int16 16 kHz samples (+ pad_samples[i] int16 zeros appended: the 600 ms flush silence)
  * -> float32 / 32768 -> SOS band-pass in float64, zero initial state, cast to float32 -> zero-padded to min_samples
  * (replaces _transcribe_with_context's numpy prologue, src/server.py:1321-1338, and _telephony_bandpass, :26-29 =

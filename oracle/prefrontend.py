@@ -199,3 +199,32 @@ def normalize_upload(audio: np.ndarray, sr: int, target_sr: int = TARGET_SR) -> 
     if a.ndim > 1:
         a = a.astype(np.float64).mean(axis=1)
     return resample_sinc_hann(a.astype(np.float32), sr, target_sr)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The SDK's long-audio splitter (split_audio_into_chunks), as the reference describes it: LEARNING_LOG.md:215-219 "sliding window
+# convolution with +/-5s search range", chunks of at most 1200 s (CLAUDE.md "up to 20min").  The SDK source is not available
+# offline, so this is a restatement of that description -- PARITY UNPINNED against the SDK.  Exact integer arithmetic defines the
+# result bit for bit: |x| -> floor(|x| * 2^40) as int64, window sums by differences of an int64 prefix sum, first minimum wins.
+def split_points(wav: np.ndarray, sr: int = TARGET_SR, max_chunk_sec: float = 1200.0, search_expand_sec: float = 5.0,
+                 min_window_ms: float = 100.0) -> np.ndarray:
+    x = np.asarray(wav, dtype=np.float32).reshape(-1)
+    n = x.shape[0]
+    max_len, expand = int(max_chunk_sec * sr), int(search_expand_sec * sr)
+    win = max(4, int((min_window_ms / 1000.0) * sr))
+    bounds, start = [0], 0
+    while n - start > max_len:
+        cut = start + max_len
+        left, right = max(start, cut - expand), min(n, cut + expand)
+        boundary = cut
+        if right - left > win:
+            q = np.floor(np.abs(x[left:right].astype(np.float64)) * float(2 ** 40)).astype(np.int64)
+            ps = np.concatenate([[0], np.cumsum(q)])
+            sums = ps[win:] - ps[:-win]
+            wstart = int(np.argmin(sums))
+            boundary = left + wstart + int(np.argmin(q[wstart:wstart + win]))
+        boundary = min(max(boundary, start + 1), n)
+        bounds.append(boundary)
+        start = boundary
+    bounds.append(n)
+    return np.asarray(bounds, dtype=np.int64)

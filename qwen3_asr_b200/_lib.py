@@ -58,6 +58,7 @@ SIGNATURES = {
     "qasr_resample_f32": (C.c_int, [_P, _P, _I64P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _P, C.c_int64, _I64P, _P]),
     "qasr_resample_f32_taps": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int)]),
+    "qasr_split_audio": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double, _I64P, C.c_int, C.POINTER(C.c_int), _P]),
     "qasr_ws_window": (C.c_int, [_P, _P, _I64P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_int, _P, C.c_int64,
                                  _I64P, _P]),
     "qasr_destroy": (None, [_P]),

@@ -48,6 +48,9 @@ cudaError_t launch_resample_f32(const float* in, const RsStream* streams_dev, in
                                 const float* taps_dev, const int* lo_dev, int n_keep, int width, int orig, int newf, float* out,
                                 int num_sms, cudaStream_t stream);
 
+// long-audio splitter: quietest sample of the quietest `win`-sample window inside [left, right) -> *boundary_out_dev
+cudaError_t launch_split_scan(const float* x, long long left, long long right, int win, long long* boundary_out_dev, cudaStream_t stream);
+
 // ---- conv1 (elementwise.cu) ------------------------------------------------------------------
 struct ChunkDesc {
   long long mel_col0;  // first mel column of the chunk in the packed mel

@@ -14,6 +14,7 @@
 // The arithmetic mirrors scipy's _sosfilt operation by operation with separately rounded multiplies and adds (no FMA
 // contraction), and the four sections are skewed across iterations (section s works on sample t - s) so that the four
 // recurrences of one iteration are independent instruction chains.
+#include <climits>
 #include <cmath>
 #include <vector>
 
@@ -156,6 +157,69 @@ __global__ void __launch_bounds__(256) downmix_f32_kernel(const float* __restric
   }
 }
 
+// ---- long-audio splitter ---------------------------------------------------------------------------
+// The SDK cuts audio longer than 1200 s at low-energy points before it is encoded (split_audio_into_chunks, described in the
+// reference's LEARNING_LOG.md:215-219: "sliding window convolution with +/-5 s search range"): for a cut wanted at sample c, look
+// at [c - expand, c + expand), take the window of `win` samples (100 ms) with the smallest sum of |x|, and cut at the quietest
+// sample inside it.  Restated here with EXACT integer arithmetic so that the result is defined bit for bit: |x| is quantised to
+// floor(|x| * 2^40) (exact for float32 inputs of magnitude >= 2^-16 at 24 significant bits; smaller samples lose their low bits
+// identically everywhere), window sums are int64, ties go to the first position (numpy argmin).  One CTA per cut: every thread
+// slides its own run of consecutive windows, then a block-wide argmin over (sum, position), then over the samples of the winner.
+constexpr int SPLIT_THREADS = 1024;
+
+__device__ __forceinline__ long long split_quant(float x) { return static_cast<long long>(floor(fabs(static_cast<double>(x)) * 1099511627776.0)); }
+
+__global__ void __launch_bounds__(SPLIT_THREADS) split_scan_kernel(const float* __restrict__ x, long long left, long long right, int win,
+                                                                    long long* __restrict__ boundary_out) {
+  __shared__ long long s_val[SPLIT_THREADS];
+  __shared__ long long s_pos[SPLIT_THREADS];
+  const int tid = threadIdx.x;
+  const long long n_win = (right - left) - win + 1;          // window start positions 0 .. n_win - 1 (relative to left)
+  const long long per = (n_win + SPLIT_THREADS - 1) / SPLIT_THREADS;
+  const long long p0 = static_cast<long long>(tid) * per, p1 = min(p0 + per, n_win);
+  long long best = LLONG_MAX, best_pos = LLONG_MAX;
+  if (p0 < p1) {
+    long long sum = 0;
+    for (int k = 0; k < win; ++k) sum += split_quant(__ldg(x + left + p0 + k));
+    best = sum;
+    best_pos = p0;
+    for (long long p = p0 + 1; p < p1; ++p) {
+      sum += split_quant(__ldg(x + left + p - 1 + win)) - split_quant(__ldg(x + left + p - 1));
+      if (sum < best) { best = sum; best_pos = p; }
+    }
+  }
+  s_val[tid] = best;
+  s_pos[tid] = best_pos;
+  __syncthreads();
+  for (int o = SPLIT_THREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) {
+      const long long v = s_val[tid + o], q = s_pos[tid + o];
+      if (v < s_val[tid] || (v == s_val[tid] && q < s_pos[tid])) { s_val[tid] = v; s_pos[tid] = q; }
+    }
+    __syncthreads();
+  }
+  const long long wstart = s_pos[0];
+  __syncthreads();
+  // quietest sample inside the winning window (first on ties)
+  best = LLONG_MAX;
+  best_pos = LLONG_MAX;
+  for (int k = tid; k < win; k += SPLIT_THREADS) {
+    const long long v = split_quant(__ldg(x + left + wstart + k));
+    if (v < best) { best = v; best_pos = k; }
+  }
+  s_val[tid] = best;
+  s_pos[tid] = best_pos;
+  __syncthreads();
+  for (int o = SPLIT_THREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) {
+      const long long v = s_val[tid + o], q = s_pos[tid + o];
+      if (v < s_val[tid] || (v == s_val[tid] && q < s_pos[tid])) { s_val[tid] = v; s_pos[tid] = q; }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *boundary_out = left + wstart + s_pos[0];
+}
+
 double bessel_i0(double x) {
   const double q = (x / 2.0) * (x / 2.0);
   double term = 1.0, s = 1.0;
@@ -273,6 +337,12 @@ cudaError_t launch_resample_pcm16(const int16_t* in, const RsStream* streams_dev
   const long long want = (max_out_len + 255) / 256;
   dim3 grid(static_cast<unsigned int>(want < 4LL * num_sms ? want : 4LL * num_sms), n_streams);
   resample_pcm16_kernel<<<grid, 256, 0, stream>>>(in, streams_dev, taps_dev, n_taps, half_len, up, down, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_scan(const float* x, long long left, long long right, int win, long long* boundary_out_dev, cudaStream_t stream) {
+  if (right - left < win || win < 1) return cudaErrorInvalidValue;
+  split_scan_kernel<<<1, SPLIT_THREADS, 0, stream>>>(x, left, right, win, boundary_out_dev);
   return cudaGetLastError();
 }
 

@@ -1569,6 +1569,48 @@ int qasr_resample_f32(qasr_handle_t h, const float* pcm_dev, const int64_t* in_o
   return stream_leave(h, stream);
 }
 
+int qasr_split_audio(qasr_handle_t h, const float* pcm_dev, int64_t n_samples, int sample_rate, double max_chunk_sec, double search_expand_sec,
+                     double min_window_ms, int64_t* boundaries_out, int capacity, int* n_chunks_out, void* stream_v) {
+  QASR_REQUIRE(h != nullptr && boundaries_out != nullptr && n_chunks_out != nullptr && n_samples >= 0, "qasr_split_audio: bad argument");
+  QASR_REQUIRE(sample_rate > 0 && max_chunk_sec > 0 && search_expand_sec >= 0 && min_window_ms > 0, "qasr_split_audio: bad parameter");
+  QASR_REQUIRE(capacity >= 2, "qasr_split_audio: capacity must hold at least [0, n_samples]");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int64_t max_len = static_cast<int64_t>(max_chunk_sec * sample_rate);
+  const int64_t expand = static_cast<int64_t>(search_expand_sec * sample_rate);
+  const int win = std::max(4, static_cast<int>((min_window_ms / 1000.0) * sample_rate));
+  QASR_REQUIRE(max_len >= 1, "qasr_split_audio: max_chunk_sec too small");
+  int n = 0;
+  boundaries_out[n++] = 0;
+  if (n_samples > max_len) {
+    QASR_REQUIRE(pcm_dev != nullptr, "qasr_split_audio: null buffer");
+    if (stream_enter(h, stream) != 0) return 2;
+    if (grow(h, &h->clipmax_buf, 64) != 0) return 2;
+    long long* d_b = static_cast<long long*>(h->clipmax_buf.p);
+    int64_t start = 0;
+    while (n_samples - start > max_len) {   // every cut depends on the previous one: a short chain of one-CTA scans
+      QASR_REQUIRE(n + 1 < capacity, "qasr_split_audio: more chunks than `capacity` boundaries");
+      const int64_t cut = start + max_len;
+      const int64_t left = std::max(start, cut - expand), right = std::min(n_samples, cut + expand);
+      long long boundary = cut;
+      if (right - left > win) {
+        QASR_LAUNCH(h, "split_scan", 4.0 * static_cast<double>(right - left), stream, launch_split_scan(pcm_dev, left, right, win, d_b, stream));
+        QASR_CUDA_CHECK(cudaMemcpyAsync(&boundary, d_b, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        QASR_CUDA_CHECK(cudaStreamSynchronize(stream));
+      }
+      boundary = std::max<long long>(boundary, start + 1);
+      boundary = std::min<long long>(boundary, n_samples);
+      boundaries_out[n++] = boundary;
+      start = boundary;
+    }
+    if (stream_leave(h, stream) != 0) return 2;
+  }
+  QASR_REQUIRE(n < capacity, "qasr_split_audio: more chunks than `capacity` boundaries");
+  boundaries_out[n++] = n_samples;
+  *n_chunks_out = n - 1;
+  return 0;
+}
+
 int qasr_ws_window(qasr_handle_t h, const int16_t* pcm16_dev, const int64_t* in_offsets, int n_streams, const int32_t* pad_samples,
                    const double* sos, int n_sections, int min_samples, float* out_dev, int64_t out_capacity, int64_t* out_offsets_out,
                    void* stream_v) {

@@ -142,6 +142,23 @@ class B200PreFrontend:
               "qasr_resample_f32")
         return out, out_offs
 
+    # ---- the SDK's long-audio splitter -----------------------------------------------------------------------------
+    def split_audio(self, pcm: torch.Tensor, max_chunk_sec: float = 1200.0, search_expand_sec: float = 5.0, min_window_ms: float = 100.0,
+                    sr: int = TARGET_SR) -> np.ndarray:
+        """mono float32 device tensor -> int64 boundaries [n_chunks + 1] (0 ... len): chunks of at most ~max_chunk_sec cut at the
+        quietest point within +/- search_expand_sec of every nominal cut (LEARNING_LOG.md:215-219).  The result is the
+        ``clip_offsets`` of ``encode_pcm_packed`` / ``B200EncoderPool.submit_pcm_host`` for the same buffer."""
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous() and pcm.dim() == 1
+        n = int(pcm.shape[0])
+        cap = n // max(1, int(max_chunk_sec * sr) - int(search_expand_sec * sr)) + 4
+        out = np.zeros(cap, dtype=np.int64)
+        nch = C.c_int(0)
+        check(self.lib, self.lib.qasr_split_audio(self.enc._h, C.c_void_p(pcm.data_ptr()), n, int(sr), float(max_chunk_sec),
+                                                  float(search_expand_sec), float(min_window_ms), out.ctypes.data_as(_lib._I64P), cap,
+                                                  C.byref(nch), self.enc._stream()),
+              "qasr_split_audio")
+        return out[: nch.value + 1].copy()
+
     def encode_uploads(self, clips: Sequence, sr: int):
         """(audio, sr) uploads -> (bf16 hidden states, token_lens): normalise, log-mel and encode without leaving the GPU."""
         pcm, offs = self.normalize_audio(clips, sr)

@@ -252,3 +252,37 @@ def test_upload_to_tokens_stays_on_the_device(pre):
     a_, b_ = hid.float().cpu().numpy(), hid2.float().cpu().numpy()
     # the two PCM inputs differ by <= 1e-6 on every sample: bf16 roundings flip here and there, nothing more
     assert np.abs(a_ - b_).max() <= 2e-2 * max(1.0, np.abs(b_).max())
+
+
+# ---- 8f-4: the SDK's long-audio splitter on the device ----------------------------------------------------------------------
+def test_split_audio_matches_the_oracle_bit_for_bit(pre):
+    from oracle import prefrontend as opf
+    from test_oracle_prefrontend import _long_signal
+
+    sr = 16000
+    cases = [
+        (_long_signal(130, 1, pauses=[(38.0, 0.4, 1e-4), (83.5, 0.3, 1e-5), (97.0, 0.5, 1e-4)]), 40.0, 5.0, 100.0),
+        (_long_signal(75, 2), 20.0, 3.0, 50.0),                       # no pauses: the minimum is wherever the noise dips
+        (np.zeros(100 * sr, np.float32), 40.0, 5.0, 100.0),           # all ties: first window, first sample
+        (_long_signal(61, 3, pauses=[(59.9, 1.1, 0.0)]), 30.0, 5.0, 100.0),   # search range clipped at the end of the audio
+        (_long_signal(30, 4), 40.0, 5.0, 100.0),                      # shorter than one chunk
+    ]
+    for x, max_s, exp_s, win_ms in cases:
+        dev = torch.from_numpy(x).to(pre.enc.tdev)
+        got = pre.split_audio(dev, max_chunk_sec=max_s, search_expand_sec=exp_s, min_window_ms=win_ms)
+        want = opf.split_points(x, sr, max_s, exp_s, win_ms)
+        assert got.tolist() == want.tolist()
+
+
+def test_split_chunks_feed_the_encoder_as_clip_offsets(pre):
+    """boundaries = clip_offsets: the chunks of a long recording are encoded as independent clips straight from the same buffer."""
+    from test_oracle_prefrontend import _long_signal
+
+    x = _long_signal(50, 7, pauses=[(14.0, 0.5, 1e-4), (31.0, 0.5, 1e-4)])
+    dev = torch.from_numpy(x).to(pre.enc.tdev)
+    b = pre.split_audio(dev, max_chunk_sec=15.0, search_expand_sec=3.0)
+    assert len(b) == 5
+    hid, toks = pre.enc.encode_pcm_packed(dev, b)
+    parts = [pre.enc.encode_pcm([x[b[i]:b[i + 1]]])[0] for i in range(len(b) - 1)]
+    torch.cuda.synchronize()
+    assert torch.equal(hid, torch.cat(parts))
