@@ -261,7 +261,7 @@ def test_split_audio_matches_the_oracle_bit_for_bit(pre):
 
     sr = 16000
     cases = [
-        (_long_signal(130, 1, pauses=[(38.0, 0.4, 1e-4), (83.5, 0.3, 1e-5), (97.0, 0.5, 1e-4)]), 40.0, 5.0, 100.0),
+        (_long_signal(130, 1, pauses=[(38.0, 0.4, 1e-4), (80.0, 0.3, 1e-5), (97.0, 0.5, 1e-4)]), 40.0, 5.0, 100.0),
         (_long_signal(75, 2), 20.0, 3.0, 50.0),                       # no pauses: the minimum is wherever the noise dips
         (np.zeros(100 * sr, np.float32), 40.0, 5.0, 100.0),           # all ties: first window, first sample
         (_long_signal(61, 3, pauses=[(59.9, 1.1, 0.0)]), 30.0, 5.0, 100.0),   # search range clipped at the end of the audio
