@@ -113,6 +113,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int kNumSMs = 148;
 
+// fixed-point scales of the integer-atomic LayerNorm statistics (epilogues.cuh RowStatsAtomic / LnFoldAcc)
+constexpr float kStatSumScale = 1048576.0f;     // 2^20: |sum of a row| < 2^43, far beyond any activation
+constexpr float kStatSqScale = 65536.0f;        // 2^16
+
 // ---- programmatic dependent launch --------------------------------------------------------------
 // The step is a chain of ~176 dependent kernels; between two of them the GPU otherwise idles for the launch latency and the
 // next kernel's prologue (barrier init, TMEM allocation, cluster sync, descriptor prefetch).  Kernels on the chain call

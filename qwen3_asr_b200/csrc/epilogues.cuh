@@ -72,6 +72,7 @@ struct EpiLinear {
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
   static constexpr bool kRowStats = false;
+  static constexpr bool kRowAtomic = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return n_valid; }
   __device__ __forceinline__ bool row_live(int) const { return true; }
@@ -176,6 +177,7 @@ struct EpiConv {
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
   static constexpr bool kRowStats = false;
+  static constexpr bool kRowAtomic = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ int n_cols() const { return c; }
   __device__ __forceinline__ bool row_live(int m) const {
@@ -211,6 +213,7 @@ struct EpiConvOut {
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
   static constexpr bool kRowStats = false;
+  static constexpr bool kRowAtomic = false;
   __device__ __forceinline__ int stats_row(int m) const { return m < m_valid ? __ldg(row_token + m) : -1; }
   __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
   __device__ __forceinline__ int n_cols() const { return d; }
@@ -247,6 +250,36 @@ struct RowStats : Base {
   float2* part;      // [rows][n_panels]
   int n_panels;      // d / 32
   static constexpr bool kRowStats = true;
+};
+
+// ... or ACCUMULATE them: every (row, 32-column panel) adds its (sum, sum of squares) to ONE pair of 64-bit integers per row with
+// atomicAdd, in fixed point (sum * 2^20, sum of squares * 2^16, each rounded to nearest).  Integer addition is associative, so the
+// totals do not depend on the order in which the CTAs arrive: deterministic and batch-invariant like everything else.  The
+// consuming GEMM (LnFoldAcc<>) reads the pair of its row in its epilogue -- nothing to finalise, no statistics kernel, no table.
+template <class Base>
+struct RowStatsAtomic : Base {
+  unsigned long long* acc;   // [rows][2], zeroed before the forward
+  float2* part = nullptr;    // unused (the kernel's non-atomic branch is compiled out)
+  int n_panels = 0;
+  static constexpr bool kRowStats = true;
+  static constexpr bool kRowAtomic = true;
+};
+template <class Base>
+struct LnFoldAcc : Base {
+  const unsigned long long* acc_p;   // [M][2]
+  const float* colsum_p;             // [N]
+  float inv_d, eps;
+  static constexpr bool kLnFold = true;
+  static constexpr bool kLnPart = false;
+  __device__ __forceinline__ const float* col_scale_ptr() const { return colsum_p; }
+  __device__ __forceinline__ float2 row_stats(int m) const {
+    if (m >= this->m_valid) return make_float2(0.f, 0.f);
+    const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(acc_p) + m);
+    const float mean = static_cast<float>(static_cast<long long>(a.x)) * (inv_d / kStatSumScale);
+    const float ex2 = static_cast<float>(static_cast<long long>(a.y)) * (inv_d / kStatSqScale);
+    const float var = fmaxf(fmaf(-mean, mean, ex2), 0.f);
+    return make_float2(mean, rsqrtf(var + eps));
+  }
 };
 
 }  // namespace qasr

@@ -182,6 +182,10 @@ cudaError_t linear_kind(const LinearArgs& a, const Epi& e, bool simt, int num_sm
 template <class Epi>
 cudaError_t linear_ln(const LinearArgs& a, const Epi& e, bool simt, int num_sms, cudaStream_t stream) {
   if (simt || a.fp8 || a.ln_colsum == nullptr) return cudaErrorNotSupported;
+  if (a.ln_acc != nullptr) {
+    LnFoldAcc<Epi> la{e, a.ln_acc, a.ln_colsum, 1.0f / static_cast<float>(a.k), 1e-5f};
+    return linear_dispatch<tc::K_BF16>(a, la, false, num_sms, stream);
+  }
   if (a.ln_part != nullptr) {
     if (a.k % 64 != 0) return cudaErrorInvalidValue;  // an even number of 32-column panels: 16-byte aligned rows of partials
     LnFoldPart<Epi> lp{{e, nullptr, a.ln_colsum}, a.ln_part, a.k / 32, 1.0f / static_cast<float>(a.k), 1e-5f};
@@ -199,16 +203,21 @@ cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_
   if (a.k % kb != 0 || a.n % 16 != 0 || (!simt && (a.bn == 0 || a.n % a.bn != 0))) return cudaErrorInvalidValue;
   if (a.fp8 && (a.row_scale == nullptr || a.col_scale == nullptr)) return cudaErrorInvalidValue;
   if (a.row_map != nullptr && a.epi != LIN_PLAIN) return cudaErrorInvalidValue;
-  if ((a.ln_stats != nullptr || a.ln_part != nullptr) && a.epi != LIN_GELU && a.epi != LIN_QKV) return cudaErrorInvalidValue;
+  const bool ln_any = a.ln_stats != nullptr || a.ln_part != nullptr || a.ln_acc != nullptr;
+  if (ln_any && a.epi != LIN_GELU && a.epi != LIN_QKV) return cudaErrorInvalidValue;
   switch (a.epi) {
     case LIN_PLAIN:
       if (a.row_map != nullptr) return linear_kind(a, EpiLinearRows{{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, a.row_map}, simt, num_sms, stream);
       return linear_kind(a, EpiLinear<ACT_NONE, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
     case LIN_GELU:
-      if (a.ln_stats != nullptr || a.ln_part != nullptr)
-        return linear_ln(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
+      if (ln_any) return linear_ln(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
       return linear_kind(a, EpiLinear<ACT_GELU, false>{a.out, a.bias, nullptr, a.ldo, a.m, a.n}, simt, num_sms, stream);
     case LIN_RESIDUAL:
+      if (a.stats_acc != nullptr) {
+        if (simt || a.fp8) return cudaErrorNotSupported;
+        RowStatsAtomic<EpiLinear<ACT_NONE, true>> e{{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, a.stats_acc};
+        return linear_dispatch<tc::K_BF16>(a, e, false, num_sms, stream);
+      }
       if (a.stats_part != nullptr) {
         if (simt || a.fp8 || a.n % 64 != 0) return cudaErrorNotSupported;
         RowStats<EpiLinear<ACT_NONE, true>> e{{a.out, a.bias, a.residual, a.ldo, a.m, a.n}, a.stats_part, a.n / 32};
@@ -218,7 +227,7 @@ cudaError_t gemm_linear(const LinearArgs& a, bool simt, int num_sms, cudaStream_
     case LIN_QKV: {
       if (a.n % 64 != 0 || a.head_rows < a.m) return cudaErrorInvalidValue;
       EpiQkv e{{a.out, a.bias, nullptr, 0, a.m, a.n}, a.head_rows};
-      if (a.ln_stats != nullptr || a.ln_part != nullptr) return linear_ln(a, e, simt, num_sms, stream);
+      if (ln_any) return linear_ln(a, e, simt, num_sms, stream);
       return linear_kind(a, e, simt, num_sms, stream);
     }
     default: return cudaErrorInvalidValue;
@@ -275,6 +284,10 @@ cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStre
     if (a.row_scale == nullptr || a.col_scale == nullptr) return cudaErrorInvalidValue;
     Scaled<EpiConvOut> se{e, a.row_scale, a.col_scale};
     return conv_out_dispatch<tc::K_E4M3>(a, se, num_sms, stream);
+  }
+  if (a.stats_acc != nullptr) {
+    RowStatsAtomic<EpiConvOut> re{e, a.stats_acc};
+    return conv_out_dispatch<tc::K_BF16>(a, re, num_sms, stream);
   }
   if (a.stats_part != nullptr) {
     RowStats<EpiConvOut> re{e, a.stats_part, a.d / 32};

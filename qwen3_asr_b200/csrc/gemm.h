@@ -58,6 +58,9 @@ struct LinearArgs {
                                // epilogue; the kernel's idle warps finalise them per tile
   // LIN_RESIDUAL, bf16 only, optional: also leave per-row / per-32-column-panel (sum, sum of squares) of the stored values
   float2* stats_part;          // [m][n / 32] or nullptr
+  // ... or accumulate them (LIN_RESIDUAL) / read them (LIN_GELU / LIN_QKV with ln_colsum) as one fixed-point pair per row
+  unsigned long long* stats_acc;        // [m][2] written with integer atomics (zeroed by the caller) or nullptr
+  const unsigned long long* ln_acc;     // [m][2] alternative to ln_stats / ln_part
   // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,
   // y = acc * row_scale[m] * col_scale[n] + bias
   int fp8;
@@ -101,6 +104,7 @@ struct ConvOutArgs {
   const float* row_scale;
   const float* col_scale;
   float2* stats_part;          // optional (bf16 only): [tokens][d / 32] partial LayerNorm statistics of the rows written
+  unsigned long long* stats_acc;   // optional (bf16 only): [tokens][2] fixed-point (sum, sum of squares), integer atomics
 };
 cudaError_t gemm_conv_out(const ConvOutArgs& a, bool simt, int num_sms, cudaStream_t stream);
 

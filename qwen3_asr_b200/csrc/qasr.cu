@@ -130,6 +130,9 @@ struct qasr_handle_s {
   float2* ln_stats = nullptr;  // [max tokens] (mean, rstd) of the residual stream's rows
   float2* ln_part = nullptr;   // [max tokens][d / 32] partial sums left by the residual epilogues (QASR_LN=stats_kernel: unused)
   bool ln_epi_stats = false;   // row statistics come from the producing GEMM's epilogue instead of a pass over x
+  bool ln_atomic = false;      // ... accumulated there with integer atomics into one (sum, sum of squares) pair per row and LayerNorm
+  unsigned long long* ln_acc = nullptr;  // [2 L + 1 LayerNorms][max tokens][2]
+  size_t ln_acc_rows = 0;
   CUtensorMap tm_x;
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
   bool use_graph = true;    // QASR_GRAPH=0: launch every kernel eagerly even for small batches (A/B, debugging)
@@ -553,12 +556,19 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     unsigned int* slot = h->fp8_per_row ? nullptr : h->amax_slots + (amax_next++ % h->n_amax_slots);
     return launch_quant_fp8(src, k, rows, k, h->a8, k, h->a_scale, slot, h->fp8_per_row, h->num_sms, stream);
   };
+  // atomic_stats: LayerNorm k of the forward (ln1 / ln2 of every layer, then ln_post) reads slot k; the epilogue that writes the
+  // residual stream before it (conv_out, out_proj, fc2) accumulates into it.  All slots are zeroed by ONE 2-D memset.
+  int ln_slot_w = 0, ln_slot_r = 0;
+  auto acc_slot = [&](int k) { return h->ln_acc + static_cast<size_t>(k) * h->ln_acc_rows * 2; };
+  if (h->ln_atomic)
+    QASR_CUDA_CHECK(cudaMemset2DAsync(h->ln_acc, h->ln_acc_rows * 16, 0, static_cast<size_t>(ntok) * 16, 2 * h->layers.size() + 1, stream));
   {
     ConvOutArgs a{};
     a.tm_a = &h->tm_act3; a.tm_b = &h->conv_out.tm; a.bn = h->conv_out.bn;
     a.a = h->act3; a.b = h->conv_out.w; a.m = nc * kTokPerChunk; a.d = d; a.k = 16 * kConvC;
     a.pe = h->pe; a.row_token = d_rt; a.tok_per_chunk = kTokPerChunk; a.out = h->x;
     if (h->ln_epi_stats) a.stats_part = h->ln_part;
+    if (h->ln_atomic) a.stats_acc = acc_slot(ln_slot_w++);
     if (h->fp8) {
       QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(h->act3, nc * kTokPerChunk, 16 * kConvC));
       a.tm_a = &h->tm_a8_conv; a.fp8 = 1; a.row_scale = h->a_scale; a.col_scale = h->conv_out.wscale;
@@ -576,8 +586,10 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
     LinearArgs la{};
     la.row_map = rmap;
     if (epi == LIN_RESIDUAL && h->ln_epi_stats) la.stats_part = h->ln_part;  // every residual GEMM writes x: the next LayerNorm's partials
+    if (epi == LIN_RESIDUAL && h->ln_atomic) la.stats_acc = acc_slot(ln_slot_w++);
     if (w.colsum != nullptr) {  // LayerNorm folded in: the operand is the residual stream itself, the epilogue applies the row statistics
-      if (h->ln_epi_stats) la.ln_part = h->ln_part;
+      if (h->ln_atomic) la.ln_acc = acc_slot(ln_slot_r++);
+      else if (h->ln_epi_stats) la.ln_part = h->ln_part;
       else la.ln_stats = h->ln_stats;
       la.ln_colsum = w.colsum;
       tm_a = &h->tm_x;
@@ -597,7 +609,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   // LayerNorm feeding a Linear: bf16 row to hbuf, or (fp8 per-row) straight to e4m3 + row scale -> returns the Linear's input
   const bool ln_fused_quant = h->fp8 && h->fp8_per_row;
   auto layernorm = [&](const float* g, const float* b) -> int {
-    if (h->ln_epi_stats) return 0;  // the consuming GEMM finalises the partials the last residual epilogue left: nothing to launch
+    if (h->ln_epi_stats || h->ln_atomic) return 0;  // the statistics come out of the last residual epilogue: nothing to launch
     if (h->ln_fold)
       QASR_LAUNCH(h, "ln_stats", 0, stream, launch_ln_stats(h->x, h->ln_stats, ntok, d, 1e-5f, stream));
     else if (ln_fused_quant)
@@ -687,7 +699,9 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->max_tokens = std::max(h->max_tokens, h->chunks_per_window * kTokPerChunk);
   // experiment / checker switches: unknown values are an error, not a silent default
   const int v_simt = env_choice("QASR_DEBUG_SIMT", {"0", "1"});
-  const int v_ln = env_choice("QASR_LN", {"stats_kernel", "unfused", "epilogue_stats"});  // stats_kernel (the default): folded LayerNorm, statistics pass
+  // folded LayerNorm with row statistics from: a separate pass (stats_kernel), per-panel partials of the residual epilogues
+  // (epilogue_stats), or their integer-atomic accumulation (atomic_stats); "unfused" = the separate LayerNorm kernel
+  const int v_ln = env_choice("QASR_LN", {"atomic_stats", "unfused", "epilogue_stats", "stats_kernel"});
   const int v_att = env_choice("QASR_ATTENTION", {"tc", "mma_sync"});
   const int v_keep = env_choice("QASR_DEBUG_KEEP", {"0", "1"});
   const int v_pdl = env_choice("QASR_PDL", {"1", "0"});
@@ -707,6 +721,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   // finalise them per tile (LnFoldPart<>): no statistics kernel at all.  Parity-green but measured no faster (12.1 vs 12.0 ms per
   // step: what the removed pass saves, the epilogues pay) -- kept as an experiment switch, off by default.
   h->ln_epi_stats = h->ln_fold && cfg->d_model % 64 == 0 && v_ln == 2;
+  h->ln_atomic = h->ln_fold && v_ln == 0;
   h->attn_simt = v_att == 1;
   h->keep_debug = v_keep == 1;
   h->use_graph = v_graph != 1;
@@ -868,6 +883,10 @@ int qasr_finalize(qasr_handle_t h) {
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->hbuf), mt * d * sizeof(bf16))) != 0) return rc;
   if (h->ln_fold && (rc = dev_alloc(h, reinterpret_cast<void**>(&h->ln_stats), mt * sizeof(float2))) != 0) return rc;
   if (h->ln_epi_stats && (rc = dev_alloc(h, reinterpret_cast<void**>(&h->ln_part), mt * (d / 32) * sizeof(float2))) != 0) return rc;
+  if (h->ln_atomic) {
+    h->ln_acc_rows = mt;
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->ln_acc), (2 * static_cast<size_t>(c.encoder_layers) + 1) * mt * 2 * sizeof(unsigned long long))) != 0) return rc;
+  }
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->qkv), mt * 3 * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->att), mt * d * sizeof(bf16))) != 0) return rc;
   if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->ffn), mt * ffn * sizeof(bf16))) != 0) return rc;

@@ -640,7 +640,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
             if (ch == 0) {
               const int srow = epi.stats_row(row0 + r);
-              if (srow >= 0) epi.part[static_cast<long long>(srow) * epi.n_panels + ((n_blk * BN + c0) >> 5)] = make_float2(s1, s2);
+              if constexpr (Epi::kRowAtomic) {
+                if (srow >= 0) {
+                  atomicAdd(epi.acc + 2 * static_cast<long long>(srow), static_cast<unsigned long long>(__float2ll_rn(s1 * kStatSumScale)));
+                  atomicAdd(epi.acc + 2 * static_cast<long long>(srow) + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kStatSqScale)));
+                }
+              } else {
+                if (srow >= 0) epi.part[static_cast<long long>(srow) * epi.n_panels + ((n_blk * BN + c0) >> 5)] = make_float2(s1, s2);
+              }
             }
           }
         }

@@ -14,6 +14,7 @@ def _make(monkeypatch, graph, cfg_name="tiny", **kw):
     from oracle import CONFIGS, make_weights
     from qwen3_asr_b200 import B200AudioEncoder
 
+    monkeypatch.delenv("QASR_DEBUG_KEEP", raising=False)    # a handle that keeps debug copies runs eagerly
     if graph is None:
         monkeypatch.delenv("QASR_GRAPH", raising=False)
     else:

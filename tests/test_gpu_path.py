@@ -39,6 +39,7 @@ def tiny():
     cfg = CONFIGS["tiny"]
     w = make_weights(cfg, seed=1)
     enc = B200AudioEncoder(cfg, w, max_chunks=64)
+    os.environ.pop("QASR_DEBUG_KEEP", None)      # read at qasr_create: must not leak into the encoders other tests create
     yield cfg, w, enc
     enc.close()
 
@@ -588,10 +589,11 @@ def test_encode_into_equals_masked_scatter(tiny):
         small.close()
 
 
-@pytest.mark.parametrize("mode", ["unfused", "stats_kernel", "epilogue_stats"])
+@pytest.mark.parametrize("mode", ["unfused", "stats_kernel", "epilogue_stats", "atomic_stats"])
 def test_layernorm_modes_agree(tiny, golden, mode):
-    """QASR_LN switches: the separate LayerNorm kernel, the folded LayerNorm with a statistics pass (default) and the folded
-    LayerNorm with statistics from the residual epilogues all meet the parity bar and agree with each other to bf16 noise."""
+    """QASR_LN switches: the separate LayerNorm kernel, the folded LayerNorm with a statistics pass, with per-panel partials from the
+    residual epilogues, and with their integer-atomic accumulation (the default) all meet the parity bar and agree with each other to
+    bf16 noise."""
     from oracle.signals import speech_like
     from qwen3_asr_b200 import B200AudioEncoder
 
@@ -613,7 +615,7 @@ def test_layernorm_modes_agree(tiny, golden, mode):
             assert range_rel(b[s:s + int(n)], golden[f"enc_tiny_{i}"]) <= HID_TOL, (mode, i)
             s += int(n)
         assert range_rel(b, a) <= HID_TOL
-        if mode == "stats_kernel":
+        if mode == "atomic_stats":
             assert np.array_equal(a, b)          # the default mode
     finally:
         other.close()
