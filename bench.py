@@ -35,8 +35,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # DRAM traffic measured once with ncu --set full (profiles/): the bench itself never runs under a profiler
-NCU_GEMM_DRAM_BYTES_PER_STEP = (3.192950 + 0.724703 + 0.782233 + 0.177196 + 0.241311 + 0.023039 + 24 * (
-    0.032128 + 0.027506 + 0.053372 + 0.000543 + 0.034240 + 0.053047 + 0.137746 + 0.013343)) * 1e9
+NCU_GEMM_DRAM_BYTES_PER_STEP = (3.864993 + 0.724993 + 0.777964 + 0.176494 + 0.238801 + 0.016801 + 24 * (
+    0.032229 + 0.027745 + 0.053576 + 0.000497 + 0.034340 + 0.050913 + 0.138404 + 0.011794)) * 1e9
 NCU_MEL_DRAM_BYTES_PER_LAUNCH = (497.989120 + 389.929216) * 1e6
 
 METRIC = "audio-sec encoded/sec (mel+encoder, 1.7B)"
@@ -500,10 +500,10 @@ def main():
             "algorithmic_flops_per_step": gemm_flops / args.steps, "launches_per_step": gemm_launches / args.steps,
             "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
             "timing": "per-launch CUDA events on the launching stream over a second pass of the same K steps",
-            # dram__bytes_read.sum + dram__bytes_write.sum of the family's 101 launches of one C2 step (conv2 3.80 GB, conv3 0.95 GB,
-            # conv_out 0.24 GB, per layer qkv 55 MB + out_proj 54 MB + fc1 81 MB + fc2 146 MB), ncu --set full, divided by 101
+            # dram__bytes_read.sum + dram__bytes_write.sum of the family's 101 launches of one C2 step (conv2 4.59 GB, conv3 0.95 GB,
+            # conv_out 0.26 GB, per layer qkv 60 MB + out_proj 54 MB + fc1 85 MB + fc2 150 MB), ncu --set full, divided by 101
             "traffic": NCU_GEMM_DRAM_BYTES_PER_STEP / 101.0 if args.config == "c2" and args.quantize is None else None,
-            "traffic_source": "profiles/r01p_gemm_raw_summary.txt (one ncu --set full capture of each kernel of the family, C2 batch)",
+            "traffic_source": "profiles/r02g_gemm_raw_summary.txt (one ncu --set full capture of each kernel of the family, C2 batch)",
         }
         kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                        "tflops": (v["work"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and k != "logmel" and v["work"] > 0 else None}
