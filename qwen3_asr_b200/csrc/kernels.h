@@ -20,8 +20,9 @@ bool build_mel_tables(mel::Tables* host_tables);
 cudaError_t upload_mel_constants(const mel::Tables* host_tables);
 // One persistent kernel over `items` (mel::Item, device).  counters: 1 + 2 * n_clips uint32 (ticket, per-clip done, per-clip max),
 // zeroed by the launcher on `stream`.
+// variant: 1 = the CTA-synchronous kernel of round 1 (three barriers per item, bulk-copied PCM slabs), 2 = warp-synchronous FFT stages
 cudaError_t launch_logmel(const float* pcm, const mel::Item* items, int n_items, const mel::Tables* tables, float* mel_out,
-                          long long mel_ld, unsigned int* counters, int n_clips, int num_sms, cudaStream_t stream);
+                          long long mel_ld, unsigned int* counters, int n_clips, int num_sms, int variant, cudaStream_t stream);
 
 // ---- WS pre-frontend (prefrontend.cu) ---------------------------------------------------------
 struct WsStream {       // one WS window

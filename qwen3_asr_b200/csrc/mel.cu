@@ -437,17 +437,239 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restr
   }
 }
 
+// ===========================================================================================================================
+// v2 (round 2, QASR_MEL=v2; NOT the default -- measured no faster): the same arithmetic, re-scheduled to
+// get rid of the barriers.  The first kernel synchronises the CTA three times
+// per 32-frame item (slab ready, exchange complete, power complete) and ncu showed 4.75 barrier-stall cycles per issued
+// instruction at 35 % issue utilisation.  Here both FFT stages are WARP-synchronous: a warp owns 4 of the item's 32 frames, reads
+// their samples straight from global memory (25 strided loads per lane, L1-resident: consecutive frames overlap by 60 %), runs
+// stage 1 (lane = (frame, j)), exchanges through its private 3.7 KB of shared memory behind a __syncwarp, runs stage 2
+// (lane = (frame, k1), 26 of 32 lanes) and leaves the power rows in a CTA-wide buffer.  ONE __syncthreads per item then starts the
+// mel phase unchanged (warp = filter group, lane = frame: compile-time unrolled filters, constant-bank weights, 128-byte stores).
+// The power buffer is double-buffered, so that barrier is the only one; clip completion is counted per warp (fence + atomic by
+// lane 0 after a __syncwarp), not per CTA.  No slab, no bulk copies, no mbarrier.
+struct MelSmem2 {
+  float2 E[THREADS / 32][2][K1][E_PITCH];   // 29.9 KB  per warp: [frame of the pair][k1][j]
+  float P[2][FB][P_PITCH];                  // 53.5 KB  double-buffered power rows of the item's 32 frames
+  Item desc[2];
+  Item deferred[MAX_DEFERRED_FWD];
+  int idx[2];
+  int n_deferred;
+  int run_clamp;
+  Item clamp;
+  float floor_v;
+};
+constexpr int kWarpsPerCta = THREADS / 32;
+static_assert(FB == 4 * kWarpsPerCta, "a warp owns four frames of an item");
+
+__global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v2(const float* __restrict__ pcm, const Item* __restrict__ items, int n_items,
+                                                               const Tables* __restrict__ tables, float* __restrict__ out, long long ld,
+                                                               unsigned int* __restrict__ ticket, unsigned int* __restrict__ clip_done,
+                                                               unsigned int* __restrict__ clip_max) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  MelSmem2& sm = *reinterpret_cast<MelSmem2*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // per-lane constants: stage 1 lane = (fr, j), stage 2 lane = (fr2, k1)
+  const int fr = lane >> 4, j = lane & 15;
+  float win[25];
+#pragma unroll
+  for (int m = 0; m < 25; ++m) win[m] = __ldg(tables->window + 16 * m + j);
+  const int fr2 = lane / K1, k1 = lane - fr2 * K1;     // lanes 26..31: fr2 == 2 -> idle in stage 2
+  float2 tw[16];
+#pragma unroll
+  for (int jj = 1; jj < 16; ++jj) tw[jj] = __ldg(&tables->tw[k1][jj]);
+
+  int t_next = 0, t_after = 0;
+  if (tid == 0) {
+    const int t0 = static_cast<int>(atomicAdd(ticket, 1u));
+    t_next = static_cast<int>(atomicAdd(ticket, 1u));
+    sm.idx[0] = t0;
+    sm.n_deferred = 0;
+    sm.run_clamp = 0;
+    if (t0 < n_items) sm.desc[0] = items[t0];
+  }
+  __syncthreads();
+  int slot = 0, pb = 0;
+
+  auto clamp_tile = [&](const Item& c, float floor_v) {
+    if (tid < c.n_frames) {
+      float* p = out + c.col0 + c.frame0 + tid;
+#pragma unroll 1
+      for (int m0 = 0; m0 < N_MELS; m0 += 16, p += 16 * ld) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __ldcg(p + i * ld);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) __stcg(p + i * ld, (fmaxf(v[i], floor_v) + 4.0f) * 0.25f);
+      }
+    }
+  };
+  // a clip is finished when every WARP of every frame item of it has stored its rows (need counts items)
+  auto clamp_ready = [&](const Item& c) { return ld_acquire_u32(clip_done + c.clip) >= static_cast<unsigned int>(c.need) * kWarpsPerCta; };
+  auto clamp_floor = [&](const Item& c) { return ordered_to_float(ld_acquire_u32(clip_max + c.clip)) - 8.0f; };
+
+  for (;;) {
+    const int idx = sm.idx[slot];
+    if (idx >= n_items) break;
+    const Item it = sm.desc[slot];
+    if (tid == 0) {   // keep two tickets ahead: the next descriptor arrives by cp.async while this item is computed
+      t_after = static_cast<int>(atomicAdd(ticket, 1u));
+      sm.idx[slot ^ 1] = t_next;
+      if (t_next < n_items) {
+        const char* src = reinterpret_cast<const char*>(items + t_next);
+        char* dst = reinterpret_cast<char*>(&sm.desc[slot ^ 1]);
+        cp_async16(dst, src);
+        cp_async16(dst + 16, src + 16);
+        cp_async16(dst + 32, src + 32);
+      }
+      t_next = t_after;
+    }
+
+    if (it.kind == 1) {
+      // ---------------- clamp item: run it if its clip is finished, otherwise set it aside (never block) ----------------
+      if (tid == 0) {
+        if (sm.n_deferred == MAX_DEFERRED) {
+          while (!clamp_ready(sm.deferred[0])) __nanosleep(100);
+        }
+        if (sm.n_deferred > 0 && clamp_ready(sm.deferred[0])) {
+          sm.clamp = sm.deferred[0];
+          for (int i = 1; i < sm.n_deferred; ++i) sm.deferred[i - 1] = sm.deferred[i];
+          sm.deferred[sm.n_deferred - 1] = it;
+          sm.floor_v = clamp_floor(sm.clamp);
+          sm.run_clamp = 1;
+        } else if (sm.n_deferred == 0 && clamp_ready(it)) {
+          sm.clamp = it;
+          sm.floor_v = clamp_floor(it);
+          sm.run_clamp = 1;
+        } else {
+          sm.deferred[sm.n_deferred++] = it;
+          sm.run_clamp = 0;
+        }
+        cp_async_wait_all();
+      }
+      __syncthreads();
+      if (sm.run_clamp) clamp_tile(sm.clamp, sm.floor_v);
+      __syncthreads();
+      slot ^= 1;
+      continue;
+    }
+
+    // ---------------- stages 1 + 2, warp-synchronous: this warp's frames 4 w .. 4 w + 3 of the item, two at a time ----------------
+    const float* clip = pcm + it.pcm_off;
+    float2* Ew = &sm.E[warp][0][0][0];
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      {
+        const int f = warp * 4 + 2 * r + fr;                       // frame of the item this lane works on in stage 1
+        const int s0 = (it.frame0 + f) * HOP - N_FFT / 2 + j;      // clip-relative index of its first sample (m = 0)
+        float v[25];
+        if (f < it.n_frames) {
+          if (s0 - j >= 0 && s0 - j + N_FFT <= it.n_samples) {     // interior frame (uniform over the 16 lanes of a frame)
+#pragma unroll
+            for (int m = 0; m < 25; ++m) v[m] = __ldg(clip + s0 + 16 * m) * win[m];
+          } else {                                                 // clip edge: reflect padding by index mirroring
+#pragma unroll
+            for (int m = 0; m < 25; ++m) v[m] = __ldg(clip + reflect_index(s0 + 16 * m, it.n_samples)) * win[m];
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < 25; ++m) v[m] = 0.f;
+        }
+        float2 V[K1];
+        rdft25(v, V);
+        float2* e = Ew + fr * K1 * E_PITCH + j;
+#pragma unroll
+        for (int q = 0; q < K1; ++q) e[q * E_PITCH] = V[q];
+      }
+      __syncwarp();
+      if (fr2 < 2) {
+        const int f = warp * 4 + 2 * r + fr2;
+        const float4* e = reinterpret_cast<const float4*>(Ew + (fr2 * K1 + k1) * E_PITCH);
+        float2 z[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 q = e[c];
+          z[2 * c] = make_float2(q.x, q.y);
+          z[2 * c + 1] = make_float2(q.z, q.w);
+        }
+#pragma unroll
+        for (int jj = 1; jj < 16; ++jj) z[jj] = cmul(z[jj], tw[jj]);
+        fft16(z);
+        float* prow = &sm.P[pb][f][0];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float pw = fmaf(z[k2].x, z[k2].x, z[k2].y * z[k2].y);
+          if (stage2_unique(k1, k2)) prow[stage2_bin(k1, k2)] = pw;
+        }
+      }
+      __syncwarp();   // E is rewritten by the next pair
+    }
+    if (tid == 0) cp_async_wait_all();   // the next descriptor has landed before the barrier publishes it
+    __syncthreads();                     // the item's 32 power rows are complete (and P[pb ^ 1] is free: everyone finished the last mel phase)
+
+    // ---------------- mel + log10: warp = filter group, lane = frame ----------------
+    {
+      const bool live = lane < it.n_frames;
+      const float* prow = &sm.P[pb][lane][0];
+      float* ocol = out + it.col0 + it.frame0 + lane;
+      float vmax = -INFINITY;
+      switch (warp) {
+        case 0: mel_group<0>(prow, ocol, ld, live, vmax); break;
+        case 1: mel_group<1>(prow, ocol, ld, live, vmax); break;
+        case 2: mel_group<2>(prow, ocol, ld, live, vmax); break;
+        case 3: mel_group<3>(prow, ocol, ld, live, vmax); break;
+        case 4: mel_group<4>(prow, ocol, ld, live, vmax); break;
+        case 5: mel_group<5>(prow, ocol, ld, live, vmax); break;
+        case 6: mel_group<6>(prow, ocol, ld, live, vmax); break;
+        default: mel_group<7>(prow, ocol, ld, live, vmax); break;
+      }
+      vmax = warp_max(live ? vmax : -INFINITY);
+      __syncwarp();   // every lane's stores are ordered before lane 0's fence
+      if (lane == 0) {
+        atomicMax(clip_max + it.clip, float_to_ordered(vmax));
+        __threadfence();
+        atomicAdd(clip_done + it.clip, 1u);
+      }
+    }
+    slot ^= 1;
+    pb ^= 1;
+  }
+
+  // no tickets left: every frame item is running or finished, so the remaining deferred clamps can simply be waited for
+  for (;;) {
+    __syncthreads();
+    if (sm.n_deferred == 0) break;
+    if (tid == 0) {
+      sm.clamp = sm.deferred[sm.n_deferred - 1];
+      while (!clamp_ready(sm.clamp)) __nanosleep(100);
+      sm.floor_v = clamp_floor(sm.clamp);
+    }
+    __syncthreads();
+    clamp_tile(sm.clamp, sm.floor_v);
+    __syncthreads();
+    if (tid == 0) --sm.n_deferred;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_logmel(const float* pcm, const mel::Item* items, int n_items, const mel::Tables* tables, float* mel_out,
-                          long long mel_ld, unsigned int* counters, int n_clips, int num_sms, cudaStream_t stream) {
+                          long long mel_ld, unsigned int* counters, int n_clips, int num_sms, int variant, cudaStream_t stream) {
   if (n_items == 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MelSmem)));
-  if (e != cudaSuccess) return e;
   // counters: [0] ticket, [1, 1 + n_clips) done, [1 + n_clips, 1 + 2 n_clips) max (ordered-uint encoding; 0 = below every float)
-  e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (1 + 2 * static_cast<size_t>(n_clips)), stream);
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (1 + 2 * static_cast<size_t>(n_clips)), stream);
   if (e != cudaSuccess) return e;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  if (variant == 2) {
+    e = cudaFuncSetAttribute(logmel_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MelSmem2)));
+    if (e != cudaSuccess) return e;
+    logmel_kernel_v2<<<grid, mel::THREADS, sizeof(MelSmem2), stream>>>(pcm, items, n_items, tables, mel_out, mel_ld, counters, counters + 1,
+                                                                       counters + 1 + n_clips);
+    return cudaGetLastError();
+  }
+  e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MelSmem)));
+  if (e != cudaSuccess) return e;
   logmel_kernel<<<grid, mel::THREADS, sizeof(MelSmem), stream>>>(pcm, items, n_items, tables, mel_out, mel_ld, counters, counters + 1,
                                                                  counters + 1 + n_clips);
   return cudaGetLastError();

@@ -135,6 +135,7 @@ struct qasr_handle_s {
   size_t ln_acc_rows = 0;
   CUtensorMap tm_x;
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
+  int mel_variant = 1;      // QASR_MEL=v2: the warp-synchronous log-mel kernel (round-2 experiment, bit-identical, not faster)
   bool use_graph = true;    // QASR_GRAPH=0: launch every kernel eagerly even for small batches (A/B, debugging)
   int chunks_per_window = 8;
   int attn_tile_rows = 128;  // token rows of the attention kernel's TMA tiles (112 when every window fits)
@@ -706,7 +707,8 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   const int v_keep = env_choice("QASR_DEBUG_KEEP", {"0", "1"});
   const int v_pdl = env_choice("QASR_PDL", {"1", "0"});
   const int v_graph = env_choice("QASR_GRAPH", {"1", "0", "all"});
-  if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0) {
+  const int v_mel = env_choice("QASR_MEL", {"v1", "v2"});
+  if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0 || v_mel < 0) {
     delete h;
     return 1;
   }
@@ -724,6 +726,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->ln_atomic = h->ln_fold && v_ln == 0;
   h->attn_simt = v_att == 1;
   h->keep_debug = v_keep == 1;
+  h->mel_variant = v_mel == 1 ? 2 : 1;
   h->use_graph = v_graph != 1;
   if (v_graph == 2) h->graph_max_chunks = 1 << 30;   // QASR_GRAPH=all: also replay large batches (the one-process pool: 8 x 176 launches per step)
 
@@ -1007,7 +1010,7 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   const double mel_bytes = 4.0 * static_cast<double>(clip_offsets[n_clips] - clip_offsets[0]) + 4.0 * mel::N_MELS * static_cast<double>(cols);
   QASR_LAUNCH(h, "logmel", mel_bytes, stream,
               launch_logmel(pcm_dev, reinterpret_cast<const mel::Item*>(st->dev), static_cast<int>(ni), h->mel_tables, mel_out_dev, mel_ld,
-                            counters, n_clips, h->num_sms, stream));
+                            counters, n_clips, h->num_sms, h->mel_variant, stream));
   if (h->capturing == nullptr) {
     QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
     st->in_flight = true;

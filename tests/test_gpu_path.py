@@ -303,7 +303,11 @@ def test_encoder_fp8_variant_vs_fp8_oracle(tiny, mode):
     from qwen3_asr_b200 import B200AudioEncoder
 
     cfg, w, _ = tiny
-    enc = B200AudioEncoder(cfg, w, max_chunks=64, quantize="fp8" if mode == "per_tensor" else "fp8_per_row")
+    os.environ["QASR_DEBUG_KEEP"] = "1"      # the test reads the post-conv_out embeddings back
+    try:
+        enc = B200AudioEncoder(cfg, w, max_chunks=64, quantize="fp8" if mode == "per_tensor" else "fp8_per_row")
+    finally:
+        os.environ.pop("QASR_DEBUG_KEEP", None)
     try:
         lens = [300, 177, 1056, 45]
         clips = [speech_like(t * 160, 60 + i) for i, t in enumerate(lens)]
@@ -619,3 +623,27 @@ def test_layernorm_modes_agree(tiny, golden, mode):
             assert np.array_equal(a, b)          # the default mode
     finally:
         other.close()
+
+
+def test_logmel_kernel_variants_are_bit_identical(tiny, golden, monkeypatch):
+    """QASR_MEL=v1 (CTA-synchronous, bulk-copied slabs: the default) and v2 (warp-synchronous FFT stages, one barrier per item: the
+    round-2 experiment) run the same arithmetic in the same order: identical bits, on the golden batch, on edge lengths and on a
+    long ragged batch."""
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import B200AudioEncoder
+
+    cfg, w, enc = tiny
+    monkeypatch.setenv("QASR_MEL", "v2")
+    old = B200AudioEncoder(cfg, w, max_chunks=16)
+    monkeypatch.delenv("QASR_MEL")
+    try:
+        names = [str(n) for n in golden["mel_names"]]
+        batches = [[_clip(golden, n) for n in names],
+                   [speech_like(n, 70 + i) for i, n in enumerate([201, 319, 320, 321, 5119, 5120, 5121, 16000 * 30, 7200, 40 * 160 + 1])]]
+        for clips in batches:
+            a, fa = enc.logmel(clips)
+            b, fb = old.logmel(clips)
+            torch.cuda.synchronize()
+            assert fa.tolist() == fb.tolist() and torch.equal(a, b)
+    finally:
+        old.close()
