@@ -54,6 +54,29 @@ struct Item {
   long long col0;     // clip start column in the packed mel
 };
 
+// v3 (the default kernel): one unit of work = 32 frames of a clip to transform (n_frames == 0: none) PLUS the clamp of a 32-frame
+// tile of a clip that finished `lag` items earlier (c_n_frames == 0: none).  Item i belongs to CTA i mod grid.
+struct Item3 {
+  int clip;
+  int frame0;           // first frame within the clip
+  int n_frames;         // valid frames (<= FB)
+  int n_samples;        // clip length in samples
+  long long pcm_off;    // clip start in the packed PCM buffer
+  long long col0;       // clip start column in the packed mel
+  int c_clip;           // clamp tile: clip, first column within the clip, width (<= FB), frame items of the clip that must be done
+  int c_frame0;
+  int c_n_frames;
+  int c_need;
+  long long c_col0;     // that clip's start column
+  long long pad_;
+};
+constexpr int P3_PITCH = 204;           // power row pitch of v3: 16-byte row loads, conflict-free for lanes = frames (204 = 12 mod 32)
+constexpr int P3_RING = 3;              // power tiles in flight per CTA
+constexpr int v3_grid(int num_sms) { return 2 * num_sms; }
+constexpr int v3_clamp_lag(int num_sms) { return 4 * v3_grid(num_sms); }   // a tile is clamped four grid-fulls of items after its clip's last one (19 MB of log-mel)
+// counters of a launch: ticket, per-clip done, per-clip max, dump word; padded so that the 16-byte poll of a done counter stays inside
+constexpr size_t counter_words(int n_clips) { return 2 * static_cast<size_t>(n_clips) + 8; }
+
 // The per-unit math is __host__ __device__ so tests/host/mel_host_test.cu executes the very same functions on the CPU.
 // ---- small complex helpers ---------------------------------------------------------------------
 __host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }

@@ -135,7 +135,7 @@ struct qasr_handle_s {
   size_t ln_acc_rows = 0;
   CUtensorMap tm_x;
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
-  int mel_variant = 1;      // QASR_MEL=v2: the warp-synchronous log-mel kernel (round-2 experiment, bit-identical, not faster)
+  int mel_variant = 3;      // QASR_MEL=v1: the CTA-synchronous, ticketed log-mel kernel of round 1 (bit-identical to the default v3)
   bool use_graph = true;    // QASR_GRAPH=0: launch every kernel eagerly even for small batches (A/B, debugging)
   int chunks_per_window = 8;
   int attn_tile_rows = 128;  // token rows of the attention kernel's TMA tiles (112 when every window fits)
@@ -157,6 +157,7 @@ struct qasr_handle_s {
   float *lnp_g = nullptr, *lnp_b = nullptr;
   LinearW proj1, proj2;
   mel::Tables* mel_tables = nullptr;
+  mel::Tables* mel_tables_host = nullptr;   // the mel weights travel as a kernel parameter of the v3 log-mel kernel
 
   // workspace
   bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr;
@@ -707,7 +708,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   const int v_keep = env_choice("QASR_DEBUG_KEEP", {"0", "1"});
   const int v_pdl = env_choice("QASR_PDL", {"1", "0"});
   const int v_graph = env_choice("QASR_GRAPH", {"1", "0", "all"});
-  const int v_mel = env_choice("QASR_MEL", {"v1", "v2"});
+  const int v_mel = env_choice("QASR_MEL", {"v3", "v1"});
   if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0 || v_mel < 0) {
     delete h;
     return 1;
@@ -726,7 +727,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->ln_atomic = h->ln_fold && v_ln == 0;
   h->attn_simt = v_att == 1;
   h->keep_debug = v_keep == 1;
-  h->mel_variant = v_mel == 1 ? 2 : 1;
+  h->mel_variant = v_mel == 1 ? 1 : 3;
   h->use_graph = v_graph != 1;
   if (v_graph == 2) h->graph_max_chunks = 1 << 30;   // QASR_GRAPH=all: also replay large batches (the one-process pool: 8 x 176 launches per step)
 
@@ -742,7 +743,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
     set_last_error("uploading the mel tables failed");
     rc = 2;
   }
-  delete host_tables;
+  if (rc == 0) h->mel_tables_host = host_tables; else delete host_tables;
   if (rc != 0) {
     qasr_destroy(h);
     return rc;
@@ -959,58 +960,110 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
   QASR_REQUIRE(pcm_dev != nullptr && mel_out_dev != nullptr, "qasr_logmel: null buffer");
   if (stream_enter(h, stream) != 0) return 2;
 
-  // Work list in ticket order: frame items clip by clip; the clamp items of a clip are emitted once kClampLag frame
-  // items of later clips lie behind it (or at the end), so that a clamp practically never waits.  Every frame item a
-  // clamp waits for has a smaller ticket, hence is running or finished: no deadlock for any grid size.
-  const size_t total = n_items * sizeof(mel::Item);
-  Staging* st = nullptr;
-  if (staging_acquire(h, total, &st) != 0) return 2;
-  mel::Item* items = reinterpret_cast<mel::Item*>(st->host);
-  const int64_t buf_samples = clip_offsets[n_clips];
-  const int kClampLag = 4 * h->num_sms;
-  size_t ni = 0;
-  long long col = 0;
-  struct Pending { int clip, t; long long col0; size_t emitted_at; };
-  std::vector<Pending> pending;
-  size_t frame_items = 0, pend_head = 0;
-  auto emit_clamps = [&](const Pending& p) {
-    const int need = (p.t + mel::FB - 1) / mel::FB;
-    for (int f0 = 0; f0 < p.t; f0 += mel::CLAMP_TILE) {
-      mel::Item& it = items[ni++];
-      it.kind = 1; it.clip = p.clip; it.frame0 = f0; it.n_frames = std::min(mel::CLAMP_TILE, p.t - f0);
-      it.n_samples = 0; it.need = need; it.bulk = 0; it.pad_ = 0; it.pcm_off = 0; it.col0 = p.col0;
-    }
-  };
-  for (int i = 0; i < n_clips; ++i) {
-    const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
-    const int t = static_cast<int>(n / mel::HOP);
-    for (int f0 = 0; f0 < t; f0 += mel::FB) {
-      mel::Item& it = items[ni++];
-      it.kind = 0; it.clip = i; it.frame0 = f0; it.n_frames = std::min(mel::FB, t - f0);
-      it.n_samples = static_cast<int>(n); it.need = 0; it.pad_ = 0; it.pcm_off = clip_offsets[i]; it.col0 = col;
-      // bulk path: no reflection for the valid frames and all 34 row copies (164 floats each) inside the PCM buffer
-      const int64_t s0 = static_cast<int64_t>(f0) * mel::HOP - mel::N_FFT / 2;
-      const int64_t need = static_cast<int64_t>(it.n_frames - 1) * mel::HOP + mel::N_FFT;
-      it.bulk = (s0 >= 0 && s0 + need <= n &&
-                 clip_offsets[i] + s0 + static_cast<int64_t>(mel::SLAB_ROWS - 1) * mel::HOP + mel::ROW_COPY <= buf_samples) ? 1 : 0;
-      ++frame_items;
-      while (pend_head < pending.size() && frame_items - pending[pend_head].emitted_at >= static_cast<size_t>(kClampLag))
-        emit_clamps(pending[pend_head++]);
-    }
-    if (t > 0) pending.push_back({i, t, col, frame_items});
-    col += t;
-  }
-  while (pend_head < pending.size()) emit_clamps(pending[pend_head++]);
-  QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
   unsigned int* counters = h->capturing != nullptr ? h->capturing->counters : nullptr;
   if (counters == nullptr) {
-    if (grow(h, &h->clipmax_buf, (2 * static_cast<size_t>(n_clips) + 1) * sizeof(unsigned int)) != 0) return 2;
+    if (grow(h, &h->clipmax_buf, mel::counter_words(n_clips) * sizeof(unsigned int)) != 0) return 2;
     counters = static_cast<unsigned int*>(h->clipmax_buf.p);
   }
   const double mel_bytes = 4.0 * static_cast<double>(clip_offsets[n_clips] - clip_offsets[0]) + 4.0 * mel::N_MELS * static_cast<double>(cols);
-  QASR_LAUNCH(h, "logmel", mel_bytes, stream,
-              launch_logmel(pcm_dev, reinterpret_cast<const mel::Item*>(st->dev), static_cast<int>(ni), h->mel_tables, mel_out_dev, mel_ld,
-                            counters, n_clips, h->num_sms, h->mel_variant, stream));
+  Staging* st = nullptr;
+  if (h->mel_variant == 3 && mel_ld < (1LL << 24)) {
+    // v3 work list: item i = the i-th 32-frame tile (clip by clip) to transform, plus the clamp of one tile whose clip finished at
+    // least `lag` items earlier (FIFO; still L2-resident unless one clip is longer than the lag).  The tiles left over at the end
+    // ride on items without frames.  Items are claimed in list order (ticket), so everything a clamp waits for has a smaller
+    // ticket, i.e. is finished or held by a running CTA: no deadlock for any grid size.
+    size_t n_tiles = 0;
+    for (int i = 0; i < n_clips; ++i) n_tiles += static_cast<size_t>(((clip_offsets[i + 1] - clip_offsets[i]) / mel::HOP + mel::FB - 1) / mel::FB);
+    const size_t lag = static_cast<size_t>(mel::v3_clamp_lag(h->num_sms));
+    const size_t total = 2 * n_tiles * sizeof(mel::Item3);   // upper bound: every tile clamped by an item of its own
+    if (staging_acquire(h, total, &st) != 0) return 2;
+    mel::Item3* items = reinterpret_cast<mel::Item3*>(st->host);
+    struct Tile { int clip, frame0, n_frames, need; long long col0; size_t eligible_at; };
+    std::vector<Tile> queue;
+    queue.reserve(n_tiles);
+    size_t q_head = 0, ni = 0;
+    long long col = 0;
+    auto attach_clamp = [&](mel::Item3& it, size_t index) {
+      if (q_head < queue.size() && queue[q_head].eligible_at <= index) {
+        const Tile& t = queue[q_head++];
+        it.c_clip = t.clip; it.c_frame0 = t.frame0; it.c_n_frames = t.n_frames; it.c_need = t.need; it.c_col0 = t.col0;
+      } else {
+        it.c_clip = 0; it.c_frame0 = 0; it.c_n_frames = 0; it.c_need = 0; it.c_col0 = 0;
+      }
+      it.pad_ = 0;
+    };
+    for (int i = 0; i < n_clips; ++i) {
+      const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
+      const int t = static_cast<int>(n / mel::HOP);
+      const int need = (t + mel::FB - 1) / mel::FB;
+      for (int f0 = 0; f0 < t; f0 += mel::FB) {
+        mel::Item3& it = items[ni];
+        it.clip = i; it.frame0 = f0; it.n_frames = std::min(mel::FB, t - f0); it.n_samples = static_cast<int>(n);
+        it.pcm_off = clip_offsets[i]; it.col0 = col;
+        attach_clamp(it, ni);
+        ++ni;
+      }
+      for (int f0 = 0; f0 < t; f0 += mel::FB) queue.push_back({i, f0, std::min(mel::FB, t - f0), need, col, ni - 1 + lag});
+      col += t;
+    }
+    while (q_head < queue.size()) {
+      mel::Item3& it = items[ni];
+      it.clip = 0; it.frame0 = 0; it.n_frames = 0; it.n_samples = 0; it.pcm_off = 0; it.col0 = 0;
+      const Tile& t = queue[q_head++];   // nothing left to wait behind: the kernel waits for the clip if it has to
+      it.c_clip = t.clip; it.c_frame0 = t.frame0; it.c_n_frames = t.n_frames; it.c_need = t.need; it.c_col0 = t.col0; it.pad_ = 0;
+      ++ni;
+    }
+    QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, ni * sizeof(mel::Item3), cudaMemcpyHostToDevice, stream));
+    QASR_LAUNCH(h, "logmel", mel_bytes, stream,
+                launch_logmel_v3(pcm_dev, reinterpret_cast<const mel::Item3*>(st->dev), static_cast<int>(ni), h->mel_tables, h->mel_tables_host,
+                                 mel_out_dev, mel_ld, counters, n_clips, h->num_sms, stream));
+  } else {
+    // Work list in ticket order: frame items clip by clip; the clamp items of a clip are emitted once kClampLag frame
+    // items of later clips lie behind it (or at the end), so that a clamp practically never waits.  Every frame item a
+    // clamp waits for has a smaller ticket, hence is running or finished: no deadlock for any grid size.
+    const size_t total = n_items * sizeof(mel::Item);
+    if (staging_acquire(h, total, &st) != 0) return 2;
+    mel::Item* items = reinterpret_cast<mel::Item*>(st->host);
+    const int64_t buf_samples = clip_offsets[n_clips];
+    const int kClampLag = 4 * h->num_sms;
+    size_t ni = 0;
+    long long col = 0;
+    struct Pending { int clip, t; long long col0; size_t emitted_at; };
+    std::vector<Pending> pending;
+    size_t frame_items = 0, pend_head = 0;
+    auto emit_clamps = [&](const Pending& p) {
+      const int need = (p.t + mel::FB - 1) / mel::FB;
+      for (int f0 = 0; f0 < p.t; f0 += mel::CLAMP_TILE) {
+        mel::Item& it = items[ni++];
+        it.kind = 1; it.clip = p.clip; it.frame0 = f0; it.n_frames = std::min(mel::CLAMP_TILE, p.t - f0);
+        it.n_samples = 0; it.need = need; it.bulk = 0; it.pad_ = 0; it.pcm_off = 0; it.col0 = p.col0;
+      }
+    };
+    for (int i = 0; i < n_clips; ++i) {
+      const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
+      const int t = static_cast<int>(n / mel::HOP);
+      for (int f0 = 0; f0 < t; f0 += mel::FB) {
+        mel::Item& it = items[ni++];
+        it.kind = 0; it.clip = i; it.frame0 = f0; it.n_frames = std::min(mel::FB, t - f0);
+        it.n_samples = static_cast<int>(n); it.need = 0; it.pad_ = 0; it.pcm_off = clip_offsets[i]; it.col0 = col;
+        // bulk path: no reflection for the valid frames and all 34 row copies (164 floats each) inside the PCM buffer
+        const int64_t s0 = static_cast<int64_t>(f0) * mel::HOP - mel::N_FFT / 2;
+        const int64_t need = static_cast<int64_t>(it.n_frames - 1) * mel::HOP + mel::N_FFT;
+        it.bulk = (s0 >= 0 && s0 + need <= n &&
+                   clip_offsets[i] + s0 + static_cast<int64_t>(mel::SLAB_ROWS - 1) * mel::HOP + mel::ROW_COPY <= buf_samples) ? 1 : 0;
+        ++frame_items;
+        while (pend_head < pending.size() && frame_items - pending[pend_head].emitted_at >= static_cast<size_t>(kClampLag))
+          emit_clamps(pending[pend_head++]);
+      }
+      if (t > 0) pending.push_back({i, t, col, frame_items});
+      col += t;
+    }
+    while (pend_head < pending.size()) emit_clamps(pending[pend_head++]);
+    QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, total, cudaMemcpyHostToDevice, stream));
+    QASR_LAUNCH(h, "logmel", mel_bytes, stream,
+                launch_logmel(pcm_dev, reinterpret_cast<const mel::Item*>(st->dev), static_cast<int>(ni), h->mel_tables, mel_out_dev, mel_ld,
+                              counters, n_clips, h->num_sms, stream));
+  }
   if (h->capturing == nullptr) {
     QASR_CUDA_CHECK(cudaEventRecord(st->ev, stream));
     st->in_flight = true;
@@ -1071,7 +1124,7 @@ int graph_dispatch(qasr_handle_t h, int kind, const void* in_dev, int mel_dtype,
     e->in_bytes = kind == GK_ENCODE_PCM ? static_cast<size_t>(samples) * sizeof(float) : static_cast<size_t>(e->in_ld) * mel::N_MELS * elt;
     e->out_bytes = static_cast<size_t>(tokens) * h->cfg.output_dim * sizeof(bf16);
     const size_t mel_bytes = kind == GK_ENCODE_PCM ? static_cast<size_t>(e->in_ld) * mel::N_MELS * sizeof(float) : 0;
-    const size_t cnt_bytes = (2 * static_cast<size_t>(n_clips) + 1) * sizeof(unsigned int);
+    const size_t cnt_bytes = mel::counter_words(n_clips) * sizeof(unsigned int);
     e->tab_cap = (256u << 10) + 256 * static_cast<size_t>(chunks) + 64 * (static_cast<size_t>(cols) / 16 + 16 * static_cast<size_t>(n_clips));
     e->bytes = e->in_bytes + e->out_bytes + mel_bytes + cnt_bytes + e->tab_cap;
     while (!h->graphs.empty() && (h->graphs.size() >= kGraphMaxEntries || h->graph_bytes + e->bytes > kGraphBytesCap)) {
@@ -1729,6 +1782,7 @@ void qasr_destroy(qasr_handle_t h) {
   if (h->ev_last != nullptr) cudaEventDestroy(h->ev_last);
   if (h->s_in != nullptr) cudaStreamDestroy(h->s_in);
   if (h->s_out != nullptr) cudaStreamDestroy(h->s_out);
+  delete h->mel_tables_host;
   delete h;
 }
 

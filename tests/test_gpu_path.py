@@ -626,20 +626,21 @@ def test_layernorm_modes_agree(tiny, golden, mode):
 
 
 def test_logmel_kernel_variants_are_bit_identical(tiny, golden, monkeypatch):
-    """QASR_MEL=v1 (CTA-synchronous, bulk-copied slabs: the default) and v2 (warp-synchronous FFT stages, one barrier per item: the
-    round-2 experiment) run the same arithmetic in the same order: identical bits, on the golden batch, on edge lengths and on a
-    long ragged batch."""
+    """QASR_MEL=v1 (round 1: CTA-synchronous, ticketed, bulk-copied slabs) and the default v3 (statically scheduled, warp-autonomous,
+    mbarrier ring of power tiles, clamp tiles riding on later items) run the same arithmetic in the same order: identical bits, on
+    the golden batch, on edge lengths, and on a batch long enough (> 3 grid-strides of items) for clamps to run in flight."""
     from oracle.signals import speech_like
     from qwen3_asr_b200 import B200AudioEncoder
 
     cfg, w, enc = tiny
-    monkeypatch.setenv("QASR_MEL", "v2")
+    monkeypatch.setenv("QASR_MEL", "v1")
     old = B200AudioEncoder(cfg, w, max_chunks=16)
     monkeypatch.delenv("QASR_MEL")
     try:
         names = [str(n) for n in golden["mel_names"]]
         batches = [[_clip(golden, n) for n in names],
-                   [speech_like(n, 70 + i) for i, n in enumerate([201, 319, 320, 321, 5119, 5120, 5121, 16000 * 30, 7200, 40 * 160 + 1])]]
+                   [speech_like(n, 70 + i) for i, n in enumerate([201, 319, 320, 321, 5119, 5120, 5121, 16000 * 30, 7200, 40 * 160 + 1])],
+                   [speech_like(n, 90 + i) for i, n in enumerate([16000 * 30] * 6 + [16000 * 7 + 13, 16000 * 29] + [16000 * 30] * 6 + [3201])]]
         for clips in batches:
             a, fa = enc.logmel(clips)
             b, fb = old.logmel(clips)
