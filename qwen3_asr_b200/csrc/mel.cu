@@ -521,7 +521,7 @@ struct MelRun3 {
     constexpr int NB2 = NB < hi ? ((hi + 3) & ~3) : NB;
     // keep the row loads where they are: hoisted to the top of the group they would hold up to 52 registers while 41 prefetched
     // values (the next round's samples, the clamp tile) wait in theirs
-    if constexpr (((M - M0) & 1) == 0) asm volatile("" ::: "memory");
+    if constexpr (((M - M0) & 3) == 0) asm volatile("" ::: "memory");
 #pragma unroll
     for (int b = NB; b < NB2; b += 4) {
       const float4 q = *reinterpret_cast<const float4*>(prow + b);
@@ -675,15 +675,17 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
           float x[25];
 #pragma unroll
           for (int m = 0; m < 25; ++m) x[m] = v[m] * u[m];
+          const float4* t4 = reinterpret_cast<const float4*>(&sm.tw[j][0]);   // [q = 2 c, 2 c + 1]; q = 0 is 1 and not applied
+          float4 t[7];                                                         // read before the transform that hides their latency
+#pragma unroll
+          for (int c = 0; c < 7; ++c) t[c] = t4[c];
           float2 V[K1];
           rdft25(x, V);
           float2* e = Ew + fr * K1 * E_PITCH + j;
-          const float4* t4 = reinterpret_cast<const float4*>(&sm.tw[j][0]);   // [q = 2 c, 2 c + 1]; q = 0 is 1 and not applied
 #pragma unroll
           for (int c = 0; c < 7; ++c) {
-            const float4 t = t4[c];
-            if (c == 0) e[0] = V[0]; else e[2 * c * E_PITCH] = cmul(V[2 * c], make_float2(t.x, t.y));
-            if (2 * c + 1 < K1) e[(2 * c + 1) * E_PITCH] = cmul(V[2 * c + 1], make_float2(t.z, t.w));
+            if (c == 0) e[0] = V[0]; else e[2 * c * E_PITCH] = cmul(V[2 * c], make_float2(t[c].x, t[c].y));
+            if (2 * c + 1 < K1) e[(2 * c + 1) * E_PITCH] = cmul(V[2 * c + 1], make_float2(t[c].z, t[c].w));
           }
         }
         bool nxt_frames = false;
