@@ -101,6 +101,14 @@ QASR_API size_t qasr_workspace_bytes(qasr_handle_t h);
  * (_get_feat_extract_output_lengths, modeling_qwen3_omni_moe.py:145-153). */
 QASR_API int64_t qasr_token_len(int64_t feature_len);
 
+/* The table behind every GELU of the device path (host-only entry point, no GPU needed; csrc/common.cuh gelu_tab).  The encoder's
+ * GELUs (ACT2FN["gelu"] = erf GELU: conv stem modeling_qwen3_omni_moe.py:693-700, fc1 :452, proj1 :760) take a value that was just
+ * rounded to bf16 and round their result to bf16, i.e. they are maps between 16-bit patterns; the device evaluates
+ * bf16(x * table[sign][clamp(|x| bits)]) and the table is built so that this IS the correctly rounded float64 erf GELU for all
+ * 65 536 inputs.  Writes the 2 x 1666 float32 ratios (positive x, then negative x; |x| bits 0x3AFF..0x4180) to table_out and
+ * returns the number of floats written, or a negative value if capacity is too small / the library's exhaustive self-check fails. */
+QASR_API int qasr_gelu_table(float* table_out, int capacity);
+
 /* Log-mel of n_clips mono 16 kHz float32 clips packed back to back on the device
  * (replaces WhisperFeatureExtractor._torch_extract_fbank_features per clip, standalone semantics).
  *   pcm_dev            float32, clip i = samples [clip_offsets[i], clip_offsets[i+1])  (host int64 [n_clips+1])

@@ -64,6 +64,36 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-a, q, fmaxf(x, 0.f));                                 // relu(x) - |x| q: no predicate, no select
 }
 
+// erf GELU of a bf16 VALUE by table (round 2).  Every GELU of the encoder takes an input that has just been rounded to bf16 and
+// rounds its output to bf16 again, so the function is a map between 16-bit patterns.  gelu(x) = x * r(x): the table holds r for the
+// |x| in [2^-9, 16) of either sign (1664 patterns each) plus one sentinel below (r = 1/2: bf16(x / 2) is the exact result for every
+// smaller |x|) and one above (r = 1 for x >= 16; r = 0 for x <= -16, so the product is -0 like torch's and NaN for -inf like torch's).
+// r(b) is the float nearest to target(b) / x(b), target = the float64 erf GELU rounded to nearest-even bf16, so bf16(x * r) IS the
+// correctly rounded GELU for every one of the 65 536 inputs (build_gelu_lut checks all of them) -- the 14-instruction formula above
+// is off by one bf16 ulp on 169 of them, torch's own float32 path on 129.  One shared-memory load + one multiply instead of 2 MUFU
+// + 12 FP32 operations.
+namespace gelu_tab {
+constexpr uint32_t A_LO = 0x3B00u;            // bf16 bits of 2^-9
+constexpr uint32_t A_HI = 0x417Fu;            // largest bf16 below 16
+constexpr int N = A_HI - A_LO + 3;            // per sign, with the two sentinels
+constexpr int WORDS = 2 * N;                  // 3332 floats = 13.3 KB
+}  // namespace gelu_tab
+bool build_gelu_lut(float* lut /* [gelu_tab::WORDS] */);   // elementwise.cu (host); false if the exhaustive check fails
+
+// ratio r for the bf16 value with bit pattern `bits16` (low 16 bits)
+__device__ __forceinline__ float gelu_ratio(const float* __restrict__ lut_s, uint32_t bits16) {
+  const uint32_t a = bits16 & 0x7fffu;
+  const uint32_t i = min(max(a, gelu_tab::A_LO - 1u), gelu_tab::A_HI + 1u) - (gelu_tab::A_LO - 1u);
+  return lut_s[(bits16 >> 15) * gelu_tab::N + i];
+}
+// two accumulators -> bf16 round -> GELU -> bf16, packed
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi);
+__device__ __forceinline__ uint32_t gelu_lut_bf16x2(const float* __restrict__ lut_s, float c0, float c1) {
+  const uint32_t p = pack_bf16x2(c0, c1);
+  const float x0 = __uint_as_float(p << 16), x1 = __uint_as_float(p & 0xffff0000u);
+  return pack_bf16x2(x0 * gelu_ratio(lut_s, p & 0xffffu), x1 * gelu_ratio(lut_s, p >> 16));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

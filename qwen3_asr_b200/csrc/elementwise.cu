@@ -6,6 +6,10 @@
 
 #include <algorithm>
 
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
 #include "kernels.h"
 #include "common.cuh"
 
@@ -432,12 +436,15 @@ __device__ __forceinline__ unsigned short mel_load_bf16_bits<__nv_bfloat16>(cons
   return *reinterpret_cast<const unsigned short*>(p);
 }
 
-template <typename MelT, int COLS>
+template <typename MelT, int COLS, bool LUT>
 __global__ void __launch_bounds__(C1M_THREADS, 2) conv1_mma_kernel(const MelT* __restrict__ mel, long long ld, const ChunkDesc* __restrict__ chunks,
                                                                   const float* __restrict__ w, const float* __restrict__ bias,
-                                                                  __nv_bfloat16* __restrict__ act1) {
+                                                                  const float* __restrict__ gelu_lut, __nv_bfloat16* __restrict__ act1) {
   constexpr int channels = 480;
   __shared__ __align__(16) unsigned short tile[C1M_TILE_H * C1M_PITCH];
+  __shared__ float lut_s[LUT ? gelu_tab::WORDS : 1];
+  if constexpr (LUT)
+    for (int i = threadIdx.x; i < gelu_tab::WORDS; i += C1M_THREADS) lut_s[i] = __ldg(gelu_lut + i);
   const int chunk = blockIdx.x;
   const int slot0 = blockIdx.y * COLS;
   const ChunkDesc cd = chunks[chunk];
@@ -503,8 +510,12 @@ __global__ void __launch_bounds__(C1M_THREADS, 2) conv1_mma_kernel(const MelT* _
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 xr = bf16_round2(c[j][2 * half], c[j][2 * half + 1]);
-          o[j] = pack_bf16x2(gelu_erf(xr.x), gelu_erf(xr.y));
+          if constexpr (LUT) {
+            o[j] = gelu_lut_bf16x2(lut_s, c[j][2 * half], c[j][2 * half + 1]);
+          } else {
+            const float2 xr = bf16_round2(c[j][2 * half], c[j][2 * half + 1]);
+            o[j] = pack_bf16x2(gelu_erf(xr.x), gelu_erf(xr.y));
+          }
         }
         *reinterpret_cast<uint4*>(dst + static_cast<long long>(h0 + g + 8 * half) * channels) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -515,24 +526,25 @@ __global__ void __launch_bounds__(C1M_THREADS, 2) conv1_mma_kernel(const MelT* _
 }  // namespace
 
 cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, const ChunkDesc* chunks, int n_chunks, const float* w,
-                         const float* bias, int channels, __nv_bfloat16* act1, bool simt, cudaStream_t stream) {
+                         const float* bias, const float* gelu_lut, int channels, __nv_bfloat16* act1, bool simt, cudaStream_t stream) {
   if (n_chunks == 0) return cudaSuccess;
   if (channels > 480 || (channels & 1)) return cudaErrorInvalidValue;
   if (!simt) {
     if (channels != 480) return cudaErrorInvalidValue;
     static_assert(ACT1_PITCH % C1M_COLS == 0 && ACT1_PITCH % C1M_COLS_SMALL == 0, "column groups tile the 52 slots");
-    if (n_chunks * (ACT1_PITCH / C1M_COLS) >= 2 * kNumSMs) {
-      dim3 grid(n_chunks, ACT1_PITCH / C1M_COLS);
-      if (mel_is_bf16)
-        conv1_mma_kernel<__nv_bfloat16, C1M_COLS><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, act1);
-      else
-        conv1_mma_kernel<float, C1M_COLS><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, act1);
-    } else {  // few chunks: more, smaller CTAs (the weight fragments are reloaded per CTA, which is noise next to an idle GPU)
-      dim3 grid(n_chunks, ACT1_PITCH / C1M_COLS_SMALL);
-      if (mel_is_bf16)
-        conv1_mma_kernel<__nv_bfloat16, C1M_COLS_SMALL><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(mel), mel_ld, chunks, w, bias, act1);
-      else
-        conv1_mma_kernel<float, C1M_COLS_SMALL><<<grid, C1M_THREADS, 0, stream>>>(static_cast<const float*>(mel), mel_ld, chunks, w, bias, act1);
+    const bool big = n_chunks * (ACT1_PITCH / C1M_COLS) >= 2 * kNumSMs;
+    // few chunks: more, smaller CTAs (the weight fragments are reloaded per CTA, which is noise next to an idle GPU)
+    const dim3 grid(n_chunks, ACT1_PITCH / (big ? C1M_COLS : C1M_COLS_SMALL));
+    auto go = [&](auto kern, auto melp) { kern<<<grid, C1M_THREADS, 0, stream>>>(melp, mel_ld, chunks, w, bias, gelu_lut, act1); };
+    const auto* mb = static_cast<const __nv_bfloat16*>(mel);
+    const auto* mf = static_cast<const float*>(mel);
+    const bool lut = gelu_lut != nullptr;
+    if (big) {
+      if (mel_is_bf16) lut ? go(conv1_mma_kernel<__nv_bfloat16, C1M_COLS, true>, mb) : go(conv1_mma_kernel<__nv_bfloat16, C1M_COLS, false>, mb);
+      else lut ? go(conv1_mma_kernel<float, C1M_COLS, true>, mf) : go(conv1_mma_kernel<float, C1M_COLS, false>, mf);
+    } else {
+      if (mel_is_bf16) lut ? go(conv1_mma_kernel<__nv_bfloat16, C1M_COLS_SMALL, true>, mb) : go(conv1_mma_kernel<__nv_bfloat16, C1M_COLS_SMALL, false>, mb);
+      else lut ? go(conv1_mma_kernel<float, C1M_COLS_SMALL, true>, mf) : go(conv1_mma_kernel<float, C1M_COLS_SMALL, false>, mf);
     }
     return cudaGetLastError();
   }
@@ -639,6 +651,50 @@ cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out
   dim3 grid(n_win, heads);
   window_attention_kernel<<<grid, ATT_WARPS * 32, smem, stream>>>(qkv, out, win, d, heads, head_rows, scale_log2e);
   return cudaGetLastError();
+}
+
+
+// ---- GELU table (common.cuh, gelu_tab): built once per handle on the host in double, then checked over all 65 536 bf16 inputs ----
+namespace {
+// round-to-nearest-even of a double to bf16 (normal and denormal range), returned as the float it is
+float bf16_rn_from_double(double v) {
+  if (v == 0.0 || std::isnan(v) || std::isinf(v)) return static_cast<float>(v);
+  int e = std::ilogb(std::fabs(v));
+  if (e < -126) e = -126;
+  const double quantum = std::ldexp(1.0, e - 7);
+  return static_cast<float>(std::nearbyint(v / quantum) * quantum);   // default rounding mode: ties to even
+}
+uint32_t f32_bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+float bits_f32(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+float bf16_rn_from_float(float f) {   // what cvt.rn.bf16x2.f32 does (finite inputs)
+  const uint32_t u = f32_bits(f);
+  return bits_f32((u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u);
+}
+}  // namespace
+
+bool build_gelu_lut(float* lut) {
+  using namespace gelu_tab;
+  auto target = [](float x) { return bf16_rn_from_double(0.5 * static_cast<double>(x) * (1.0 + std::erf(static_cast<double>(x) * 0.70710678118654752440))); };
+  for (int sgn = 0; sgn < 2; ++sgn) {
+    float* t = lut + sgn * N;
+    t[0] = 0.5f;
+    t[N - 1] = sgn ? 0.0f : 1.0f;
+    for (uint32_t a = A_LO; a <= A_HI; ++a) {
+      const float x = bits_f32(((sgn ? 0x8000u : 0u) | a) << 16);
+      t[a - (A_LO - 1)] = static_cast<float>(static_cast<double>(target(x)) / static_cast<double>(x));
+    }
+  }
+  // the device evaluates bf16_rn(x * r): it must be the correctly rounded GELU for EVERY finite input
+  for (uint32_t b = 0; b < 65536u; ++b) {
+    const float x = bits_f32(b << 16);
+    if (std::isnan(x) || std::isinf(x)) continue;
+    const uint32_t a = b & 0x7fffu;
+    const uint32_t i = std::min(std::max(a, A_LO - 1u), A_HI + 1u) - (A_LO - 1u);
+    const float got = bf16_rn_from_float(x * lut[(b >> 15) * N + i]);
+    const float want = target(x);
+    if (f32_bits(got) != f32_bits(want) && !(got == 0.f && want == 0.f)) return false;
+  }
+  return true;
 }
 
 }  // namespace qasr

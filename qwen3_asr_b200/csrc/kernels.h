@@ -64,7 +64,7 @@ struct ChunkDesc {
 constexpr int ACT1_PITCH = 52;  // columns per chunk in conv1's output: [zero][50][zero]
 constexpr int ACT1_H = 64;
 cudaError_t launch_conv1(const void* mel, int mel_is_bf16, long long mel_ld, const ChunkDesc* chunks, int n_chunks,
-                         const float* w /*[C][9]*/, const float* bias /*[C]*/, int channels,
+                         const float* w /*[C][9]*/, const float* bias /*[C]*/, const float* gelu_lut /*[gelu_tab::WORDS], device*/, int channels,
                          __nv_bfloat16* act1, bool simt /*fp32 FFMA checker instead of the mma.sync kernel*/, cudaStream_t stream);
 
 // ---- FP8 dynamic quantisation (quant.cu) -----------------------------------------------------

@@ -148,6 +148,10 @@ struct qasr_handle_s {
 
   // parameters
   float *conv1_w = nullptr, *conv1_b = nullptr;
+  float* gelu_lut = nullptr;   // common.cuh gelu_tab: the correctly rounded bf16 erf GELU as a table of ratios
+  bool gelu_by_table = true;   // QASR_GELU=formula: conv1 evaluates the closed-form approximation like the GEMM epilogues (A/B).  The table
+                               // was also tried in the fc1 epilogue: 2.36 -> 2.45 ms (its bank-conflicted loads compete with the operand
+                               // traffic of the tensor pipe for shared-memory bandwidth), so the GEMM epilogues keep the formula
   bf16 *conv2_w = nullptr, *conv3_w = nullptr;
   float *conv2_b = nullptr, *conv3_b = nullptr;
   CUtensorMap tm_conv2_w, tm_conv3_w;
@@ -534,7 +538,7 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   double att_flops = 0;
   for (const int2& w : mb.win) att_flops += 4.0 * w.y * w.y * d;
   QASR_LAUNCH(h, "conv1", px1 * kConvC * 18.0, stream,
-              launch_conv1(mel, mel_is_bf16, mel_ld, d_cd, nc, h->conv1_w, h->conv1_b, kConvC, h->act1, h->simt, stream));
+              launch_conv1(mel, mel_is_bf16, mel_ld, d_cd, nc, h->conv1_w, h->conv1_b, h->gelu_by_table ? h->gelu_lut : nullptr, kConvC, h->act1, h->simt, stream));
   {
     ConvArgs a{};
     a.tm_a = &h->tm_act1; a.tm_b = &h->tm_conv2_w;
@@ -709,7 +713,8 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   const int v_pdl = env_choice("QASR_PDL", {"1", "0"});
   const int v_graph = env_choice("QASR_GRAPH", {"1", "0", "all"});
   const int v_mel = env_choice("QASR_MEL", {"v3", "v1"});
-  if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0 || v_mel < 0) {
+  const int v_gelu = env_choice("QASR_GELU", {"table", "formula"});
+  if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0 || v_mel < 0 || v_gelu < 0) {
     delete h;
     return 1;
   }
@@ -728,6 +733,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->attn_simt = v_att == 1;
   h->keep_debug = v_keep == 1;
   h->mel_variant = v_mel == 1 ? 1 : 3;
+  h->gelu_by_table = v_gelu == 0;
   h->use_graph = v_graph != 1;
   if (v_graph == 2) h->graph_max_chunks = 1 << 30;   // QASR_GRAPH=all: also replay large batches (the one-process pool: 8 x 176 launches per step)
 
@@ -744,6 +750,14 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
     rc = 2;
   }
   if (rc == 0) h->mel_tables_host = host_tables; else delete host_tables;
+  if (rc == 0) {
+    std::vector<float> lut(gelu_tab::WORDS);
+    if (!build_gelu_lut(lut.data())) {
+      set_last_error("the GELU table failed its exhaustive check against the float64 erf GELU");
+      rc = 2;
+    }
+    if (rc == 0) rc = upload_f32(h, lut.data(), lut.size(), &h->gelu_lut);
+  }
   if (rc != 0) {
     qasr_destroy(h);
     return rc;
@@ -929,6 +943,11 @@ int qasr_finalize(qasr_handle_t h) {
   QASR_CUDA_CHECK(cudaDeviceSynchronize());
   h->finalized = true;
   return 0;
+}
+
+int qasr_gelu_table(float* table_out, int capacity) {
+  if (table_out == nullptr || capacity < gelu_tab::WORDS) return -1;
+  return build_gelu_lut(table_out) ? gelu_tab::WORDS : -2;
 }
 
 size_t qasr_workspace_bytes(qasr_handle_t h) { return h == nullptr ? 0 : h->device_bytes; }

@@ -147,6 +147,32 @@ def test_fast_gelu_formula_over_all_bf16_inputs():
     assert mism <= 2 * max(torch_mism, 100), (mism, torch_mism)
 
 
+def test_gelu_table_is_the_correctly_rounded_erf_gelu(lib):
+    """qasr_gelu_table (host-only): bf16(x * ratio) over EVERY finite bf16 input equals the float64 erf GELU rounded to bf16 -- what
+    the device evaluates in conv1 (one shared-memory load and one multiply per value).  torch's own float32 path misses that on
+    ~129 inputs by one ulp, the closed-form approximation kept for the GEMM epilogues on 169."""
+    import ctypes as C
+
+    import torch
+
+    buf = np.zeros(4096, dtype=np.float32)
+    n = lib.qasr_gelu_table(buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size)
+    assert n == 2 * 1666
+    tab = buf[:n].reshape(2, 1666)
+    bits = np.arange(65536, dtype=np.uint32)
+    x = (bits << 16).view(np.float32)
+    fin = np.isfinite(x)
+    a = bits & 0x7FFF
+    idx = np.clip(a, 0x3B00 - 1, 0x417F + 1) - (0x3B00 - 1)
+    with np.errstate(invalid="ignore"):
+        y = (x * tab[bits >> 15, idx]).astype(np.float32)
+    got = torch.from_numpy(y[fin]).to(torch.bfloat16)
+    ref = torch.nn.functional.gelu(torch.from_numpy(x[fin]).double()).to(torch.bfloat16)   # float64 -> bf16, one rounding
+    assert torch.equal(got.float(), ref.float())
+    # sentinels: tiny inputs halve exactly, x >= 16 passes through, x <= -16 gives -0
+    assert tab[0, 0] == 0.5 and tab[1, 0] == 0.5 and tab[0, -1] == 1.0 and tab[1, -1] == 0.0
+
+
 def test_pool_sharding_rule_on_the_host(lib):
     """qasr_pool_plan = the rule qasr_pool_submit shards by: contiguous clip ranges, near-equal mel-frame counts, every clip placed,
     empty ranges only when there are fewer clips than devices.  Pure host code: runs without a GPU."""
