@@ -71,6 +71,7 @@ struct EpiLinear {
   struct Prefetch { uint4 r; };
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
+  static constexpr bool kLnPart = false;
   static constexpr bool kRowStats = false;
   static constexpr bool kRowAtomic = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
@@ -176,6 +177,7 @@ struct EpiConv {
   typedef NoPrefetch Prefetch;
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
+  static constexpr bool kLnPart = false;
   static constexpr bool kRowStats = false;
   static constexpr bool kRowAtomic = false;
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
@@ -212,6 +214,7 @@ struct EpiConvOut {
   struct Prefetch { float4 a, b; };
   static constexpr bool kScaled = false;
   static constexpr bool kLnFold = false;
+  static constexpr bool kLnPart = false;
   static constexpr bool kRowStats = false;
   static constexpr bool kRowAtomic = false;
   __device__ __forceinline__ int stats_row(int m) const { return m < m_valid ? __ldg(row_token + m) : -1; }

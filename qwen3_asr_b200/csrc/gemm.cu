@@ -6,6 +6,7 @@
 
 #include "epilogues.cuh"
 #include "tc_gemm.cuh"
+#include "tc_gemm_small.cuh"
 
 namespace qasr {
 
@@ -82,6 +83,8 @@ int make_tmap_conv(CUtensorMap* tm, const void* base, long long g_in, int h_in, 
   return 0;
 }
 
+int pick_bn_small(int n, int k) { return (k % tc::BLOCK_K == 0 && n % 32 == 0) ? 32 : 0; }
+
 int pick_bn(int n) {
   if (n % 256 == 0) return 256;
   if (n % 128 == 0) return 128;
@@ -137,6 +140,22 @@ cudaError_t launch_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const tc
   }
 }
 
+// one CTA per BN-column slice of the weight, the whole slice resident (tc_gemm_small.cuh)
+template <int BN, class Epi>
+cudaError_t launch_small(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int n_tiles, int num_kb, const Epi& epi, cudaStream_t stream) {
+  using L = tc::SmallLayout<BN>;
+  auto kern = tc::gemm_smallm_kernel<BN, Epi>;
+  const int smem = L::total(num_kb);
+  if (num_kb > tc::kSmallMaxKb || smem > 232448) return cudaErrorInvalidValue;
+  static thread_local int attr_set = 0;   // the attribute is per function and device; the largest request wins
+  if (attr_set < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set = 232448;
+  }
+  return launch_pdl(kern, dim3(n_tiles), dim3(tc::kSmallThreads), smem, stream, 1, tm_a, tm_b, num_kb, epi);
+}
+
 template <class ALoad, class Epi>
 cudaError_t launch_simt(const ALoad& aload, const __nv_bfloat16* b, long long ldb, int m, int n, int k, const Epi& epi, cudaStream_t stream) {
   const long long items = static_cast<long long>(m) * (n / 8);
@@ -154,16 +173,28 @@ cudaError_t linear_dispatch(const LinearArgs& a, const Epi& epi, bool simt, int 
     tc::ALoadLinear al{a.a, a.lda, a.m};
     return launch_simt(al, a.b, a.ldb, a.m, a.n, a.k, epi, stream);
   }
+  int bn = a.bn;
+  const CUtensorMap* tm_b = a.tm_b;
+  if constexpr (KIND == tc::K_BF16 && !Epi::kScaled && !Epi::kLnPart) {
+    // a single window or chunk (the unbatched reference's call shape) is latency-bound on 256-column tiles.  K <= 1024: the
+    // small-M kernel (tc_gemm_small.cuh), one CTA per 32-column weight slice.  Longer K (fc2): the slice would not fit shared
+    // memory, and 16-column slices would change the 32-column granularity at which the residual epilogues round their LayerNorm
+    // partial sums (bit-exact batch invariance) -- the pair kernel on 64-column tiles instead: twice the pairs at work.
+    if (a.m <= tc::BLOCK_M && a.tm_b_small != nullptr && a.bn_small == 32) {
+      if (a.k <= 1024) return launch_small<32>(*a.tm_a, *a.tm_b_small, a.n / 32, a.k / tc::BLOCK_K, epi, stream);
+      if (kGemmCta2 && a.n % 64 == 0) { bn = 64; tm_b = a.tm_b_small; }   // a pair stages 2 x 32 weight rows: the same box
+    }
+  }
   tc::GemmShape sh{};
   sh.m_tiles = (a.m + tc::BLOCK_M - 1) / tc::BLOCK_M;
-  sh.n_tiles = a.n / a.bn;
+  sh.n_tiles = a.n / bn;
   sh.num_kb = a.k / tc::block_k_elems<KIND>();
   sh.kb_per_tap = 1;
   sh.gt = 1;
-  switch (a.bn) {
-    case 256: return launch_tc<256, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
-    case 128: return launch_tc<128, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
-    case 64: return launch_tc<64, tc::A_LINEAR, KIND>(*a.tm_a, *a.tm_b, sh, epi, num_sms, stream);
+  switch (bn) {
+    case 256: return launch_tc<256, tc::A_LINEAR, KIND>(*a.tm_a, *tm_b, sh, epi, num_sms, stream);
+    case 128: return launch_tc<128, tc::A_LINEAR, KIND>(*a.tm_a, *tm_b, sh, epi, num_sms, stream);
+    case 64: return launch_tc<64, tc::A_LINEAR, KIND>(*a.tm_a, *tm_b, sh, epi, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -22,6 +22,8 @@ int make_tmap_conv(CUtensorMap* tm, const void* base, long long g_in, int h_in, 
 
 // Largest supported N tile (256 / 128 / 64) that divides n; 0 if none.
 int pick_bn(int n);
+// Box rows of the small-M weight map for an [n, k] weight: 32 if it divides n; 0 if the path does not apply.
+int pick_bn_small(int n, int k);
 
 // The GEMM family runs as CTA pairs (tcgen05.mma.cta_group::2, see tc_gemm.cuh) unless the library is built with
 // -DQASR_GEMM_1CTA=1 (A/B builds).  In pair mode each CTA stages half of the weight tile, so the weight tensor maps
@@ -61,6 +63,10 @@ struct LinearArgs {
   // ... or accumulate them (LIN_RESIDUAL) / read them (LIN_GELU / LIN_QKV with ln_colsum) as one fixed-point pair per row
   unsigned long long* stats_acc;        // [m][2] written with integer atomics (zeroed by the caller) or nullptr
   const unsigned long long* ln_acc;     // [m][2] alternative to ln_stats / ln_part
+  // small-M path (m <= 128, bf16): the same weight with a box of bn_small = 32 rows: the small-M kernel (tc_gemm_small.cuh) for
+  // k <= 1024, 64-column tiles of the pair kernel beyond; nullptr = not offered
+  const CUtensorMap* tm_b_small;
+  int bn_small;
   // FP8 variant (QUANTIZE=fp8): tm_a / tm_b are e4m3 maps (make_tmap_rowmajor_u8), k counts e4m3 elements,
   // y = acc * row_scale[m] * col_scale[n] + bias
   int fp8;

@@ -80,6 +80,8 @@ struct LinearW {
   float* colsum = nullptr; // [n] LayerNorm-folded Linears: column sums of the gamma-scaled bf16 weight
   int n = 0, k = 0, bn = 0;
   CUtensorMap tm;          // over w or w8
+  int bn_s = 0;            // small-M path (bf16 only): N slice per CTA (16 / 32), 0 = not offered
+  CUtensorMap tm_s;        // the same weight with a box of bn_s rows
 };
 
 struct LayerW {
@@ -149,6 +151,7 @@ struct qasr_handle_s {
   // parameters
   float *conv1_w = nullptr, *conv1_b = nullptr;
   float* gelu_lut = nullptr;   // common.cuh gelu_tab: the correctly rounded bf16 erf GELU as a table of ratios
+  bool small_m = true;         // QASR_SMALL_M=0: calls of <= 128 tokens also go through the persistent pair kernel (A/B)
   bool gelu_by_table = true;   // QASR_GELU=formula: conv1 evaluates the closed-form approximation like the GEMM epilogues (A/B).  The table
                                // was also tried in the fc1 epilogue: 2.36 -> 2.45 ms (its bank-conflicted loads compete with the operand
                                // traffic of the tensor pipe for shared-memory bandwidth), so the GEMM epilogues keep the formula
@@ -402,6 +405,13 @@ int upload_bf16(qasr_handle_s* h, const float* src, size_t n, bf16** dst) {
 }
 
 // nn.Linear [n, k] (+ bias) -> device weight (bf16, or e4m3 + scales in fp8 mode), f32 bias, TMA map with box rows = bn.
+// the small-M kernel (tc_gemm_small.cuh) reads the same bf16 weight through a box of 16 / 32 rows
+int make_small_tmap(qasr_handle_s* h, LinearW* out) {
+  out->bn_s = h->small_m ? pick_bn_small(out->n, out->k) : 0;
+  if (out->bn_s == 0) return 0;
+  return make_tmap_rowmajor(&out->tm_s, out->w, out->n, out->k, out->k, out->bn_s);
+}
+
 // `modules`: number of nn.Linear modules stacked along n (3 for the fused q|k|v weight): each owns its per-tensor scale.
 // ln_g / ln_b (both or neither): fold the LayerNorm that feeds this Linear into it (handles with ln_fold): the device weight becomes
 // bf16(gamma[k] * bf16(w[n, k])), colsum[n] its row sums, and the bias absorbs beta: b'[n] = b[n] + sum_k beta[k] * bf16(w[n, k]).
@@ -430,7 +440,8 @@ int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, 
     if (upload_f32(h, bias.data(), n, &out->b) != 0) return 2;
     if (upload_f32(h, colsum.data(), n, &out->colsum) != 0) return 2;
     if (upload_bf16(h, wf.data(), nk, &out->w) != 0) return 2;
-    return make_tmap_rowmajor(&out->tm, out->w, n, k, k, gemm_b_box_rows(out->bn));
+    if (make_tmap_rowmajor(&out->tm, out->w, n, k, k, gemm_b_box_rows(out->bn)) != 0) return 2;
+    return make_small_tmap(h, out);
   }
   if (b != nullptr && upload_f32(h, b, n, &out->b) != 0) return 2;
   if (h->fp8) {
@@ -447,7 +458,8 @@ int make_linear(qasr_handle_s* h, const float* w, const float* b, int n, int k, 
     return make_tmap_rowmajor_u8(&out->tm, out->w8, n, k, k, gemm_b_box_rows(out->bn));
   }
   if (upload_bf16(h, w, static_cast<size_t>(n) * k, &out->w) != 0) return 2;
-  return make_tmap_rowmajor(&out->tm, out->w, n, k, k, gemm_b_box_rows(out->bn));
+  if (make_tmap_rowmajor(&out->tm, out->w, n, k, k, gemm_b_box_rows(out->bn)) != 0) return 2;
+  return make_small_tmap(h, out);
 }
 
 // ln_prefix: name of the LayerNorm module whose output this Linear consumes ("" = none) -- folded in on handles with ln_fold
@@ -587,6 +599,26 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
   // ---- transformer layers
   // one nn.Linear: (fp8: quantise the bf16 input first) GEMM with fused bias / GELU / residual epilogue
   // a_raw == nullptr: the producer (LayerNorm) has already left the quantised input and its row scales in h->a8 / h->a_scale
+  // A call of <= 128 tokens reads its activations through maps whose HEIGHT is the token count: rows beyond it are out of bounds,
+  // i.e. zero-filled by the TMA unit without a byte of L2 traffic.  Every CTA of a small-M GEMM streams the whole [128, K]
+  // activation through its own SM's L2 port (~120 GB/s): at 65 tokens that is half the bytes of the capacity-high maps.
+  CUtensorMap sm_h, sm_x, sm_att, sm_ffn;
+  const bool small_maps = h->small_m && ntok <= 128;
+  if (small_maps) {
+    int rc2;
+    if ((rc2 = make_tmap_rowmajor(&sm_h, h->hbuf, ntok, d, d, 128)) != 0) return rc2;
+    if ((rc2 = make_tmap_rowmajor(&sm_x, h->x, ntok, d, d, 128)) != 0) return rc2;
+    if ((rc2 = make_tmap_rowmajor(&sm_att, h->att, ntok, d, d, 128)) != 0) return rc2;
+    if ((rc2 = make_tmap_rowmajor(&sm_ffn, h->ffn, ntok, c.encoder_ffn_dim, c.encoder_ffn_dim, 128)) != 0) return rc2;
+  }
+  auto small_map = [&](const CUtensorMap* tm) -> const CUtensorMap* {
+    if (!small_maps) return tm;
+    if (tm == &h->tm_h) return &sm_h;
+    if (tm == &h->tm_x) return &sm_x;
+    if (tm == &h->tm_att) return &sm_att;
+    if (tm == &h->tm_ffn) return &sm_ffn;
+    return tm;
+  };
   auto linear = [&](const char* name, double flops, const CUtensorMap* tm_a, const bf16* a_raw, const LinearW& w, int epi, bf16* o,
                     long long ldo, const bf16* residual, const long long* rmap = nullptr) -> int {
     LinearArgs la{};
@@ -601,9 +633,11 @@ int run_microbatch(qasr_handle_s* h, const void* mel, int mel_is_bf16, long long
       tm_a = &h->tm_x;
       a_raw = h->x;
     }
+    if (!h->fp8) tm_a = small_map(tm_a);
     la.tm_a = tm_a; la.tm_b = &w.tm; la.bn = w.bn; la.a = a_raw; la.lda = w.k; la.b = w.w; la.ldb = w.k;
     la.m = ntok; la.n = w.n; la.k = w.k; la.epi = epi; la.out = o; la.ldo = ldo; la.bias = w.b; la.residual = residual;
     la.head_rows = h->head_rows;
+    if (w.bn_s != 0 && !h->ln_epi_stats) { la.tm_b_small = &w.tm_s; la.bn_small = w.bn_s; }   // taken by gemm_linear when ntok <= 128
     if (h->fp8) {
       if (a_raw != nullptr) QASR_LAUNCH(h, "quant_fp8", 0, stream, quant(a_raw, ntok, w.k));
       la.tm_a = w.k == d ? &h->tm_a8_d : &h->tm_a8_ffn;
@@ -714,7 +748,8 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   const int v_graph = env_choice("QASR_GRAPH", {"1", "0", "all"});
   const int v_mel = env_choice("QASR_MEL", {"v3", "v1"});
   const int v_gelu = env_choice("QASR_GELU", {"table", "formula"});
-  if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0 || v_mel < 0 || v_gelu < 0) {
+  const int v_small = env_choice("QASR_SMALL_M", {"1", "0"});
+  if (v_simt < 0 || v_ln < 0 || v_att < 0 || v_keep < 0 || v_pdl < 0 || v_graph < 0 || v_mel < 0 || v_gelu < 0 || v_small < 0) {
     delete h;
     return 1;
   }
@@ -734,6 +769,7 @@ int qasr_create(const qasr_config_t* cfg, int device, qasr_handle_t* out) {
   h->keep_debug = v_keep == 1;
   h->mel_variant = v_mel == 1 ? 1 : 3;
   h->gelu_by_table = v_gelu == 0;
+  h->small_m = v_small == 0 && !h->fp8;
   h->use_graph = v_graph != 1;
   if (v_graph == 2) h->graph_max_chunks = 1 << 30;   // QASR_GRAPH=all: also replay large batches (the one-process pool: 8 x 176 launches per step)
 

@@ -110,6 +110,8 @@ QASR_DEFINE_MBAR_WAIT(wait_tmem_empty)  // MMA issuer: epilogue has drained the 
 QASR_DEFINE_MBAR_WAIT(wait_tmem_full)   // epilogue: the tile's last MMA has completed
 QASR_DEFINE_MBAR_WAIT(wait_stats_full)  // epilogue: the tile's row statistics are in the smem table (LnFoldPart)
 QASR_DEFINE_MBAR_WAIT(wait_stats_empty) // statistics warps: the table slot has been read
+QASR_DEFINE_MBAR_WAIT(wait_small_empty) // small-M kernel, TMA producer: activation stage freed
+QASR_DEFINE_MBAR_WAIT(wait_small_full)  // small-M kernel: weight k-block / activation stage / accumulator has landed
 #undef QASR_DEFINE_MBAR_WAIT
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -290,8 +292,10 @@ struct SmemLayout {
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
+// pair mode: six 32 KB stages at BN = 256; a 64-column tile stages 20 KB, and nine of them (the K = 3584 / 4096 fc2 of a single
+// window runs on such tiles and is bound by the latency of its ring, see gemm.cu) still fit
 template <int BN, bool CTA2 = false>
-constexpr int default_stages() { return CTA2 ? 6 : (BN > 192 ? 4 : (BN > 128 ? 4 : 6)); }
+constexpr int default_stages() { return CTA2 ? (BN <= 64 ? 9 : 6) : (BN > 192 ? 4 : (BN > 128 ? 4 : 6)); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
@@ -301,6 +305,120 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One 32-column panel of the epilogue, executed by ONE warp (lane = accumulator row in phase A): shared by the persistent
+// pair kernel below and the small-M kernel (tc_gemm_small.cuh).
+//   taddr_c0   TMEM address of the panel's first column in this warp's lane quarter
+//   ncol0      global output column of the panel's first column;  ncols <= 32 valid columns
+//   row0       global output row of lane 0;  bs_tab / ss_tab: the panel's bias / per-column table entries in shared memory
+// ---------------------------------------------------------------------------------------------
+template <class Epi>
+__device__ __forceinline__ void epilogue_panel(const Epi& epi, uint32_t taddr_c0, int ncols, int row0, int ncol0, bool live, float row_scale,
+                                               float2 ln, const float* bs_tab, const float* ss_tab, uint32_t stage_base, int lane) {
+  const int sub = lane >> 2, ch = lane & 3;  // phase B: row within an 8-row group, 16-byte chunk of the 64-byte row segment
+    // destinations of phase B + prefetch of the post-rounding addend (hidden behind phase A)
+    long long offs[4];
+    typename Epi::Prefetch pre[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = row0 + i * 8 + sub;
+      const int n = ncol0 + ch * 8;
+      offs[i] = ch * 8 < ncols ? epi.offset(m, n) : -1;
+      if (offs[i] >= 0) pre[i] = epi.prefetch(m, n, offs[i]);
+    }
+    // phase A: TMEM -> registers -> bias / activation -> bf16 -> staging (row = lane, 64-byte rows whose 16-byte
+    // chunks are XOR-swizzled with (row >> 1) & 3: conflict-free for the row-per-lane writes and the phase-B reads)
+    uint32_t v[kPanel];
+#pragma unroll
+    for (int g = 0; g < kPanel / 16; ++g)
+      if (g * 16 < ncols) tmem_ld16(taddr_c0 + g * 16, v + g * 16);
+    tmem_ld_wait();
+    const float* bs = bs_tab;
+    const float* ss = ss_tab;
+#pragma unroll
+    for (int j = 0; j < kPanel / 8; ++j) {
+      if (j * 8 < ncols) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bs + j * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bs + j * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(v[j * 8 + e]);
+        if constexpr (Epi::kScaled) {  // dequantise: acc * (activation row scale * weight column scale)
+          const float4 s0 = *reinterpret_cast<const float4*>(ss + j * 8);
+          const float4 s1 = *reinterpret_cast<const float4*>(ss + j * 8 + 4);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] *= row_scale * sc[e];
+        }
+        float pre_act[8];  // the module output before its bf16 rounding
+        if constexpr (Epi::kLnFold) {  // rstd * acc + (bias' - rstd * mean * colsum[n]): two FMAs per output
+          const float4 s0 = *reinterpret_cast<const float4*>(ss + j * 8);
+          const float4 s1 = *reinterpret_cast<const float4*>(ss + j * 8 + 4);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pre_act[e] = fmaf(acc[e], ln.y, fmaf(-ln.x, sc[e], bb[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pre_act[e] = acc[e] + bb[e];
+        }
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float2 r = bf16_round2(pre_act[e], pre_act[e + 1]);
+          o[e] = live ? epi.act(r.x) : 0.f;
+          o[e + 1] = live ? epi.act(r.y) : 0.f;
+        }
+        uint4 pk;
+        pk.x = pack_bf16x2(o[0], o[1]);
+        pk.y = pack_bf16x2(o[2], o[3]);
+        pk.z = pack_bf16x2(o[4], o[5]);
+        pk.w = pack_bf16x2(o[6], o[7]);
+        st_shared_v4(stage_base + lane * (kPanel * 2) + ((j ^ ((lane >> 1) & 3)) << 4), pk);
+      }
+    }
+    __syncwarp();
+    // phase B: each instruction moves eight complete 64-byte row segments
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (!Epi::kRowStats) {
+        if (offs[i] >= 0) {
+          const int r = i * 8 + sub;
+          const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
+          epi.finish(offs[i], sv, pre[i]);
+        }
+      } else {
+        // ... and leaves the row's partial LayerNorm statistics of this 32-column panel (sum, sum of squares of the stored bf16
+        // values): the four lanes of a row add up through two shuffles, lane ch == 0 writes the fixed slot part[row][panel]
+        const int r = i * 8 + sub;
+        float s1 = 0.f, s2 = 0.f;
+        if (offs[i] >= 0) {
+          const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
+          const uint4 fin = epi.finish(offs[i], sv, pre[i]);
+          const float2 a = unpack_bf16x2(fin.x), b = unpack_bf16x2(fin.y), c = unpack_bf16x2(fin.z), d2 = unpack_bf16x2(fin.w);
+          s1 = ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d2.x + d2.y));
+          s2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c.x, c.x, fmaf(c.y, c.y, fmaf(d2.x, d2.x, d2.y * d2.y)))))));
+        }
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        if (ch == 0) {
+          const int srow = epi.stats_row(row0 + r);
+          if constexpr (Epi::kRowAtomic) {
+            if (srow >= 0) {
+              atomicAdd(epi.acc + 2 * static_cast<long long>(srow), static_cast<unsigned long long>(__float2ll_rn(s1 * kStatSumScale)));
+              atomicAdd(epi.acc + 2 * static_cast<long long>(srow) + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kStatSqScale)));
+            }
+          } else {
+            if (srow >= 0) epi.part[static_cast<long long>(srow) * epi.n_panels + ((ncol0) >> 5)] = make_float2(s1, s2);
+          }
+        }
+      }
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -507,7 +625,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
     float* scale_s = reinterpret_cast<float*>(smem + L::SCALE_OFFSET);
     constexpr int NP = (BN + kPanel - 1) / kPanel;
-    const int sub = lane >> 2, ch = lane & 3;  // phase B: row within an 8-row group, 16-byte chunk of the 64-byte row segment
     int iter = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
       const int m_blk = CTA2 ? 2 * (tile / shape.n_tiles) + rank : tile / shape.n_tiles;
@@ -551,107 +668,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int p = pw; p < NP; p += kEpiWarps / 4) {
         const int c0 = p * kPanel;
         const int ncols = BN - c0 < kPanel ? BN - c0 : kPanel;
-        // destinations of phase B + prefetch of the post-rounding addend (hidden behind phase A)
-        long long offs[4];
-        typename Epi::Prefetch pre[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int m = row0 + i * 8 + sub;
-          const int n = n_blk * BN + c0 + ch * 8;
-          offs[i] = ch * 8 < ncols ? epi.offset(m, n) : -1;
-          if (offs[i] >= 0) pre[i] = epi.prefetch(m, n, offs[i]);
-        }
-        // phase A: TMEM -> registers -> bias / activation -> bf16 -> staging (row = lane, 64-byte rows whose 16-byte
-        // chunks are XOR-swizzled with (row >> 1) & 3: conflict-free for the row-per-lane writes and the phase-B reads)
-        uint32_t v[kPanel];
-#pragma unroll
-        for (int g = 0; g < kPanel / 16; ++g)
-          if (g * 16 < ncols) tmem_ld16(taddr + c0 + g * 16, v + g * 16);
-        tmem_ld_wait();
-        const float* bs = bias_s + tab * 256 + c0;
-        const float* ss = scale_s + tab * 256 + c0;
-#pragma unroll
-        for (int j = 0; j < kPanel / 8; ++j) {
-          if (j * 8 < ncols) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bs + j * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bs + j * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float acc[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(v[j * 8 + e]);
-            if constexpr (Epi::kScaled) {  // dequantise: acc * (activation row scale * weight column scale)
-              const float4 s0 = *reinterpret_cast<const float4*>(ss + j * 8);
-              const float4 s1 = *reinterpret_cast<const float4*>(ss + j * 8 + 4);
-              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) acc[e] *= row_scale * sc[e];
-            }
-            float pre_act[8];  // the module output before its bf16 rounding
-            if constexpr (Epi::kLnFold) {  // rstd * acc + (bias' - rstd * mean * colsum[n]): two FMAs per output
-              const float4 s0 = *reinterpret_cast<const float4*>(ss + j * 8);
-              const float4 s1 = *reinterpret_cast<const float4*>(ss + j * 8 + 4);
-              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pre_act[e] = fmaf(acc[e], ln.y, fmaf(-ln.x, sc[e], bb[e]));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pre_act[e] = acc[e] + bb[e];
-            }
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const float2 r = bf16_round2(pre_act[e], pre_act[e + 1]);
-              o[e] = live ? epi.act(r.x) : 0.f;
-              o[e + 1] = live ? epi.act(r.y) : 0.f;
-            }
-            uint4 pk;
-            pk.x = pack_bf16x2(o[0], o[1]);
-            pk.y = pack_bf16x2(o[2], o[3]);
-            pk.z = pack_bf16x2(o[4], o[5]);
-            pk.w = pack_bf16x2(o[6], o[7]);
-            st_shared_v4(stage_base + lane * (kPanel * 2) + ((j ^ ((lane >> 1) & 3)) << 4), pk);
-          }
-        }
-        __syncwarp();
-        // phase B: each instruction moves eight complete 64-byte row segments
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if constexpr (!Epi::kRowStats) {
-            if (offs[i] >= 0) {
-              const int r = i * 8 + sub;
-              const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
-              epi.finish(offs[i], sv, pre[i]);
-            }
-          } else {
-            // ... and leaves the row's partial LayerNorm statistics of this 32-column panel (sum, sum of squares of the stored bf16
-            // values): the four lanes of a row add up through two shuffles, lane ch == 0 writes the fixed slot part[row][panel]
-            const int r = i * 8 + sub;
-            float s1 = 0.f, s2 = 0.f;
-            if (offs[i] >= 0) {
-              const uint4 sv = ld_shared_v4(stage_base + r * (kPanel * 2) + ((ch ^ ((r >> 1) & 3)) << 4));
-              const uint4 fin = epi.finish(offs[i], sv, pre[i]);
-              const float2 a = unpack_bf16x2(fin.x), b = unpack_bf16x2(fin.y), c = unpack_bf16x2(fin.z), d2 = unpack_bf16x2(fin.w);
-              s1 = ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d2.x + d2.y));
-              s2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c.x, c.x, fmaf(c.y, c.y, fmaf(d2.x, d2.x, d2.y * d2.y)))))));
-            }
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-            if (ch == 0) {
-              const int srow = epi.stats_row(row0 + r);
-              if constexpr (Epi::kRowAtomic) {
-                if (srow >= 0) {
-                  atomicAdd(epi.acc + 2 * static_cast<long long>(srow), static_cast<unsigned long long>(__float2ll_rn(s1 * kStatSumScale)));
-                  atomicAdd(epi.acc + 2 * static_cast<long long>(srow) + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * kStatSqScale)));
-                }
-              } else {
-                if (srow >= 0) epi.part[static_cast<long long>(srow) * epi.n_panels + ((n_blk * BN + c0) >> 5)] = make_float2(s1, s2);
-              }
-            }
-          }
-        }
-        __syncwarp();
+        epilogue_panel(epi, taddr + c0, ncols, row0, n_blk * BN + c0, live, row_scale, ln, bias_s + tab * 256 + c0, scale_s + tab * 256 + c0, stage_base,
+                       lane);
       }
       tc_fence_before();
       __syncwarp();

@@ -130,3 +130,41 @@ def test_real_width_single_window_graph(monkeypatch):
     finally:
         eager.close()
         graphed.close()
+
+
+@pytest.mark.parametrize("model", ["0.6B", "1.7B"])
+def test_small_m_path_is_bit_identical(monkeypatch, model):
+    """Calls of <= 128 tokens (one window / one chunk: what the unbatched reference sends, src/server.py:79-94) take the small-M GEMM
+    kernel (tc_gemm_small.cuh: one CTA per 16/32-column weight slice, the whole slice requested up front).  Same K order, same
+    epilogue code: bit-identical to the persistent pair kernel (QASR_SMALL_M=0), so a window alone still equals the window in a
+    batch -- checked at the real model widths for 1 .. 9 one-second chunks, eager and graph-replayed."""
+    from oracle.signals import speech_like
+    from qwen3_asr_b200 import B200AudioEncoder
+    from qwen3_asr_b200.synth import model_config, random_weights
+
+    cfg = dict(model_config(model))
+    cfg["encoder_layers"] = 3
+    w = random_weights(cfg, seed=3)
+    monkeypatch.setenv("QASR_SMALL_M", "0")
+    big = B200AudioEncoder(cfg, w, max_chunks=64)
+    monkeypatch.delenv("QASR_SMALL_M")
+    small = B200AudioEncoder(cfg, w, max_chunks=64)
+    try:
+        for i, secs in enumerate([0.45, 1.0, 2.45, 5.0, 6.0, 8.99, 9.84]):      # 6 .. 128 tokens
+            clip = [speech_like(int(secs * 16000), 40 + i)]
+            want, t0 = big.encode_pcm(clip)
+            for rep in range(3):                                                 # eager, capture, replay
+                got, t1 = small.encode_pcm(clip)
+                torch.cuda.synchronize()
+                assert t0.tolist() == t1.tolist() and int(t0[0]) <= 128
+                assert torch.equal(got, want), (model, secs, rep)
+        # and inside a batch (pair kernel on both handles) the same clip gives the same rows
+        clips = [speech_like(int(s * 16000), 40 + i) for i, s in enumerate([0.45, 1.0, 2.45, 5.0, 6.0, 8.99, 9.84])]
+        both, toks = small.encode_pcm(clips)
+        alone, _ = small.encode_pcm([clips[3]])
+        torch.cuda.synchronize()
+        o = int(sum(toks[:3]))
+        assert torch.equal(both[o:o + int(toks[3])], alone)
+    finally:
+        big.close()
+        small.close()
