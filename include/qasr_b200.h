@@ -155,6 +155,9 @@ QASR_API int qasr_encode_pcm_host(qasr_handle_t h, const float* pcm_host, const 
 QASR_API int qasr_submit_pcm_host(qasr_handle_t h, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                          int64_t out_capacity_tokens, int64_t* token_lens_out, void* stream, uint64_t* ticket_out);
 QASR_API int qasr_wait(qasr_handle_t h, uint64_t ticket);
+/* Non-blocking form of qasr_wait: *done_out = 1 once out_host holds the batch of `ticket` (a qasr_wait would return at once), else 0.
+ * What an event loop -- or the pool's worker threads -- call between other work instead of parking a thread in qasr_wait. */
+QASR_API int qasr_poll(qasr_handle_t h, uint64_t ticket, int* done_out);
 /* Device-side durations of the three legs of a finished ticket (CUDA events on the copy-in, compute and copy-out streams): host->device
  * copy, log-mel + encoder, device->host copy.  Valid after qasr_wait(ticket) until the same slot's next submit (ticket + 2). */
 QASR_API int qasr_pipe_times(qasr_handle_t h, uint64_t ticket, float* h2d_ms, float* compute_ms, float* d2h_ms);

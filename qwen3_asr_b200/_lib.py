@@ -49,6 +49,7 @@ SIGNATURES = {
     "qasr_encode_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P]),
     "qasr_submit_pcm_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P, C.POINTER(C.c_uint64)]),
     "qasr_wait": (C.c_int, [_P, C.c_uint64]),
+    "qasr_poll": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int)]),
     "qasr_pipe_times": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "qasr_submit_clips_host": (C.c_int, [_P, _P, _I64P, _I64P, _I64P, C.c_int, _P, C.c_int64, _I64P, _P, C.POINTER(C.c_uint64)]),
     "qasr_logmel_host": (C.c_int, [_P, _P, _I64P, C.c_int, _P, _I64P, _P]),

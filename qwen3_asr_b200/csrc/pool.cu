@@ -139,6 +139,20 @@ void worker_main(qasr_pool_s* p, Worker* w) {
     {
       std::unique_lock<std::mutex> lk(p->mu);
       p->cv_work.wait(lk, [&] { return p->stop || !w->queue.empty() || !w->inflight.empty(); });
+      if (w->queue.empty() && w->inflight.size() == 1 && !p->stop) {
+        // One shard in flight, nothing queued: do NOT park in qasr_wait -- the caller's next batch typically arrives a moment after
+        // it has collected the previous one, and a worker blocked for the ~12 ms of the running shard would enqueue it (host
+        // launches + H2D, ~1.7 ms) only after the GPU had gone idle.  Wait for new work, looking at the shard now and then.
+        p->cv_work.wait_for(lk, std::chrono::microseconds(100), [&] { return p->stop || !w->queue.empty(); });
+        if (w->queue.empty() && !p->stop) {
+          int done = 0;
+          const uint64_t t = w->inflight.front().handle_ticket;
+          lk.unlock();
+          const int rc = qasr_poll(w->handle, t, &done);
+          lk.lock();
+          if (rc == 0 && done == 0) continue;
+        }
+      }
       if (!w->queue.empty() && w->inflight.size() < 2) {
         s = std::move(w->queue.front());
         w->queue.pop_front();

@@ -1513,6 +1513,20 @@ int qasr_wait(qasr_handle_t h, uint64_t ticket) {
   return 0;
 }
 
+int qasr_poll(qasr_handle_t h, uint64_t ticket, int* done_out) {
+  QASR_REQUIRE(h != nullptr && done_out != nullptr, "qasr_poll: bad argument");
+  *done_out = 1;
+  if (ticket == 0) return 0;
+  QASR_REQUIRE(ticket < h->next_ticket, "qasr_poll: unknown ticket");
+  DeviceGuard guard(h->device);
+  qasr_handle_s::Pipe& pp = h->pipe[ticket & 1];
+  if (pp.seq == 0) return 0;
+  const cudaError_t e = cudaEventQuery(pp.ev_out);   // (a later ticket of the same slot: its event covers this one, as in qasr_wait)
+  if (e == cudaErrorNotReady) { *done_out = 0; return 0; }
+  QASR_CUDA_CHECK(e);
+  return 0;
+}
+
 int qasr_pipe_times(qasr_handle_t h, uint64_t ticket, float* h2d_ms, float* compute_ms, float* d2h_ms) {
   QASR_REQUIRE(h != nullptr && ticket != 0 && ticket < h->next_ticket, "qasr_pipe_times: unknown ticket");
   DeviceGuard guard(h->device);
