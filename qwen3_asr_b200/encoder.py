@@ -272,6 +272,12 @@ class B200AudioEncoder:
     def wait(self, ticket: int) -> None:
         check(self.lib, self.lib.qasr_wait(self._h, C.c_uint64(int(ticket))), "qasr_wait")
 
+    def poll(self, ticket: int) -> bool:
+        """Non-blocking: has ``out_host`` of ``ticket`` been filled?  (``wait`` would return at once.)"""
+        done = C.c_int(0)
+        check(self.lib, self.lib.qasr_poll(self._h, C.c_uint64(int(ticket)), C.byref(done)), "qasr_poll")
+        return bool(done.value)
+
     def logmel_host(self, clips: Sequence[np.ndarray]):
         offs = np.zeros(len(clips) + 1, dtype=np.int64)
         for i, c in enumerate(clips):

@@ -291,6 +291,28 @@ def test_pipelined_submit_wait_matches_synchronous_call(tiny):
     enc.wait(tickets[-1])
     for a, b in zip(ref, outs):
         assert torch.equal(a, b)
+    # qasr_poll: the non-blocking form -- false while the batch is in flight at least once for a long one, true in the end, and
+    # once it says true the output is complete without a qasr_wait
+    import time
+
+    big = [speech_like(16000 * 30, 990 + i) for i in range(6)]
+    offs = np.zeros(len(big) + 1, dtype=np.int64)
+    offs[1:] = np.cumsum([c.shape[0] for c in big])
+    pcm = torch.from_numpy(np.concatenate(big)).pin_memory()
+    n_tok = sum(enc.token_len(c.shape[0] // 160) for c in big)
+    want = torch.empty((n_tok, enc.output_dim), dtype=torch.bfloat16).pin_memory()
+    enc.encode_pcm_host(pcm, offs, want)
+    got = torch.zeros_like(want).pin_memory()
+    t, _ = enc.submit_pcm_host(pcm, offs, got)
+    first = enc.poll(t)
+    deadline = time.time() + 30.0
+    while not enc.poll(t):
+        assert time.time() < deadline
+        time.sleep(0.0002)
+    assert torch.equal(got, want)
+    assert enc.poll(t) and enc.poll(0)
+    enc.wait(t)
+    assert first in (False, True)   # (almost always False: 180 s of audio take longer than the call's return)
 
 
 @pytest.mark.parametrize("mode", ["per_tensor", "per_row"])
