@@ -147,12 +147,9 @@ cudaError_t launch_small(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int n
   auto kern = tc::gemm_smallm_kernel<BN, Epi>;
   const int smem = L::total(num_kb);
   if (num_kb > tc::kSmallMaxKb || smem > 232448) return cudaErrorInvalidValue;
-  static thread_local int attr_set = 0;   // the attribute is per function and device; the largest request wins
-  if (attr_set < smem) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return e;
-    attr_set = 232448;
-  }
+  // the attribute is per function AND device: set it on every launch like launch_tc does (a host-side table lookup)
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
   return launch_pdl(kern, dim3(n_tiles), dim3(tc::kSmallThreads), smem, stream, 1, tm_a, tm_b, num_kb, epi);
 }
 
