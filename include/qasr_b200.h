@@ -252,7 +252,9 @@ QASR_API size_t qasr_pool_workspace_bytes(qasr_pool_t p);
 /* qasr_submit_pcm_host across the pool.  Returns at once; token_lens_out [n_clips] and (optionally) clip_device_out
  * [n_clips] (the CUDA device each clip was sent to) are filled before it returns and not touched afterwards (clip_offsets
  * is copied).  pcm_host and out_host must stay valid until qasr_pool_collect(ticket) returns; any number of batches may be in flight (each worker
- * keeps two on its GPU).  out_host: bf16 [sum tokens, output_dim] in clip order. */
+ * keeps two on its GPU).  For throughput keep THREE batches in flight (collect the oldest, submit the next): with two, every GPU's next
+ * shard is submitted only after the previous batch has been collected, i.e. one device->host copy late (measured on 8 B200s: 613 k
+ * audio-s/s with three, 542 k with two).  out_host: bf16 [sum tokens, output_dim] in clip order. */
 QASR_API int qasr_pool_submit(qasr_pool_t p, const float* pcm_host, const int64_t* clip_offsets, int n_clips, void* out_host,
                               int64_t out_capacity_tokens, int64_t* token_lens_out, int32_t* clip_device_out, uint64_t* ticket_out);
 QASR_API int qasr_pool_collect(qasr_pool_t p, uint64_t ticket);
