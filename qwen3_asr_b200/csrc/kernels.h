@@ -23,7 +23,7 @@ cudaError_t upload_mel_constants(const mel::Tables* host_tables);
 // variant: 1 = the CTA-synchronous kernel of round 1 (three barriers per item, bulk-copied PCM slabs), 2 = warp-synchronous FFT stages
 cudaError_t launch_logmel(const float* pcm, const mel::Item* items, int n_items, const mel::Tables* tables, float* mel_out,
                           long long mel_ld, unsigned int* counters, int n_clips, int num_sms, cudaStream_t stream);
-// v3 (default): statically scheduled, warp-autonomous; its own item format (mel::Item3), same counters block
+// v3 (default): ticketed, warp-autonomous (no CTA barrier); its own item format (mel::Item3), counters of mel::counter_words(n_clips)
 cudaError_t launch_logmel_v3(const float* pcm, const mel::Item3* items, int n_items, const mel::Tables* tables, const mel::Tables* host_tables,
                              float* mel_out, long long mel_ld, unsigned int* counters, int n_clips, int num_sms, cudaStream_t stream);
 

@@ -441,8 +441,9 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restr
 // v3 (round 2, the default; QASR_MEL=v1 selects the kernel above): the same arithmetic, re-scheduled so that NO warp ever waits
 // at a CTA-wide barrier.  ncu on v1: 35 % issue utilisation, 4.75 barrier-stall cycles per issued instruction (three
 // __syncthreads per 32-frame item at 16 warps per SM).  Here
-//   * work is assigned statically (item i -> CTA i mod grid) and every warp walks its CTA's list on its own: descriptors are read
-//     straight from global memory one item ahead, no ticket, no broadcast;
+//   * items are still claimed through the global ticket (a static i -> CTA i mod grid assignment let CTAs drift apart and spin on
+//     clips other CTAs had not finished), but by ONE lane, two items ahead, with the 64-byte descriptor bulk-copied into a ring
+//     behind an mbarrier: no broadcast barrier, and every warp walks the ring on its own;
 //   * both FFT stages are warp-synchronous: a warp owns 4 of the item's 32 frames (two rounds of two), stage 1 lane = (frame, j)
 //     reads its 25 strided samples from global memory (L1-resident: consecutive frames overlap by 60 %) ONE ROUND AHEAD into
 //     registers, applies the stage-2 twiddle to its own 12 outputs (32 busy lanes instead of stage 2's 26), and exchanges through
@@ -452,11 +453,14 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restr
 //     the slowest warp of the PREVIOUS item -- a whole item of slack;
 //   * the mel phase reads the power row with 16-byte loads (row pitch 204: conflict-free for lane = frame) interleaved with the
 //     compile-time unrolled filters, and takes the clip maximum BEFORE the logarithm (lg2 is monotone) with FMNMX3;
-//   * the max-8 clamp is no longer a work item of its own: every item carries the 32-frame tile of the item `lag` positions
-//     before it (long finished, still in L2) and each warp rewrites 16 of the tile's 128 rows; the completion signal of a warp
-//     (fence + atomic) is deferred to its next mel phase, when the stores it covers have long drained.
-// Dependencies point to strictly smaller item indices and a CTA finishes the pending mel phase before it looks at a clamp, so
-// the grid cannot deadlock whatever subset of it is resident.
+//   * the max-8 clamp is no longer a work item of its own: every item carries the 32-frame tile of an item `lag` tickets before
+//     it (its clip finished, the tile still in L2) and each warp rewrites 16 of the tile's 128 rows.  The clip's counter is polled
+//     with relaxed loads / a 16-byte bulk copy and the tile read with .cg loads: an acquire would invalidate the L1 that holds the
+//     re-read PCM, and an ordinary load would share a scoreboard with the sample loads in flight;
+//   * a tile's completion signal (clip maximum, then a release increment: ~1 us of round trip for the warp that sends it) is owed
+//     by warp (tile mod 8) and leaves from a later FFT, as soon as the tile's `empty` barrier is complete.
+// Dependencies point to strictly smaller tickets, a warp runs its pending mel phase and sends what it owes before it waits for a
+// clip, and a claimed ticket belongs to a resident CTA: the grid cannot deadlock whatever subset of it is resident.
 constexpr int TW_PITCH = 14;               // float2 per twiddle row (13 used): 112 B, same bank pattern as the window rows
 constexpr int WIN_PITCH = 28;              // window row pitch: 16-byte loads, conflict-free for the 16 lanes of a frame (28 = -4 mod 32)
 constexpr int D3_RING = 8;                 // descriptor ring (items in flight per CTA: the current one, two published ahead, slack)

@@ -55,7 +55,7 @@ struct Item {
 };
 
 // v3 (the default kernel): one unit of work = 32 frames of a clip to transform (n_frames == 0: none) PLUS the clamp of a 32-frame
-// tile of a clip that finished `lag` items earlier (c_n_frames == 0: none).  Item i belongs to CTA i mod grid.
+// tile of a clip that finished `lag` items earlier (c_n_frames == 0: none).  Items are claimed in list order through a ticket.
 struct Item3 {
   int clip;
   int frame0;           // first frame within the clip

@@ -648,7 +648,7 @@ def test_layernorm_modes_agree(tiny, golden, mode):
 
 
 def test_logmel_kernel_variants_are_bit_identical(tiny, golden, monkeypatch):
-    """QASR_MEL=v1 (round 1: CTA-synchronous, ticketed, bulk-copied slabs) and the default v3 (statically scheduled, warp-autonomous,
+    """QASR_MEL=v1 (round 1: CTA-synchronous, ticketed, bulk-copied slabs) and the default v3 (ticketed, warp-autonomous,
     mbarrier ring of power tiles, clamp tiles riding on later items) run the same arithmetic in the same order: identical bits, on
     the golden batch, on edge lengths, and on a batch long enough (> 3 grid-strides of items) for clamps to run in flight."""
     from oracle.signals import speech_like
