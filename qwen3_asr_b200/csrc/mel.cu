@@ -12,6 +12,7 @@
 // item a clamp waits for has a smaller ticket and is therefore already running or finished -> no deadlock, no second
 // kernel, and the log-mel makes one trip to DRAM.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -486,6 +487,34 @@ static_assert(sizeof(Item3) == 64, "Item3 is bulk-copied: a multiple of 16 bytes
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+// Bounded wait for the v3 kernel: a protocol bug traps (-> a CUDA error the host reports) instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity);
+// (no printf: a call in this kernel costs the register allocator 8 % of the kernel's speed; the trap surfaces as a launch failure)
+__device__ __forceinline__ void mel_wait_timeout(int) { __trap(); }
+// mbarrier wait of the v3 kernel.  Product build: the three-instruction try_wait loop -- counting the attempts (to trap on a protocol
+// bug instead of hanging) costs this issue-bound kernel 3.5 % (A/B on one box: 0.528 vs 0.547 ms), with or without a suspend-time
+// hint; -DQASR_MEL_BOUNDED=1 builds the counted version for bring-up.  The one wait that depends on OTHER CTAs (a clip's completion
+// counter) is always bounded.
+__device__ __forceinline__ void mbar_wait3(unsigned long long* bar, uint32_t parity, int what) {
+#ifdef QASR_MEL_BOUNDED
+  const uint32_t addr = smem_addr(bar);
+  for (unsigned int spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 27)) mel_wait_timeout(what);
+  }
+#else
+  (void)what;
+  mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {   // non-blocking
   uint32_t ok;
   asm volatile(
@@ -597,7 +626,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
   int t_next = 0, t_after = 0;
   auto publish = [&](int seq) {                         // lane 0 of warp 0 only
     const int slot = seq % D3_RING, use = seq / D3_RING;
-    if (use > 0) mbar_wait(&sm.ring_empty[slot], (use - 1) & 1);   // every warp is done with the slot's previous item
+    if (use > 0) mbar_wait3(&sm.ring_empty[slot], (use - 1) & 1, 1);   // every warp is done with the slot's previous item
     const int t = t_next;
     t_next = t_after;
     t_after = static_cast<int>(atomicAdd(ticket, 1u));  // consumed by the next call: the round trip is never waited for
@@ -626,7 +655,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
   auto send_signal = [&](bool wait) {
     if (owe_n >= 0) {
       const int s = owe_n % P3_RING;
-      if (wait) mbar_wait(&sm.empty[s], (owe_n / P3_RING) & 1);
+      if (wait) mbar_wait3(&sm.empty[s], (owe_n / P3_RING) & 1, 2);
       if (lane == 0) {
         const float vmax = lg2_fast(__uint_as_float(atomicExch(&sm.mel_amax[s], 0u))) * 0.30102999566398120f;
         atomicMax(clip_max + owe_clip, float_to_ordered(vmax));
@@ -648,7 +677,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
     const int dslot = seq % D3_RING;
     if (more) {
       if (tid == 0) publish(seq + 2);
-      mbar_wait(&sm.ring_full[dslot], (seq / D3_RING) & 1);
+      mbar_wait3(&sm.ring_full[dslot], (seq / D3_RING) & 1, 3);
       more = sm.ring[dslot].n_frames >= 0;
     }
     const Item3& cur = sm.ring[dslot];
@@ -663,7 +692,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
       // ---------------- stages 1 + 2, warp-synchronous: this warp's frames 4 w .. 4 w + 3 of the item, two at a time ----------------
       slot = n_fft % P3_RING;
       use = n_fft / P3_RING;
-      if (use > 0) mbar_wait(&sm.empty[slot], (use - 1) & 1);
+      if (use > 0) mbar_wait3(&sm.empty[slot], (use - 1) & 1, 4);
       float2* Ew = &sm.E[warp][0][0][0];
       // round -1 only loads (the first item of the CTA, or after items without frames)
 #pragma unroll 1
@@ -710,7 +739,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
           }
         }
         if (r == 1) {
-          mbar_wait(&sm.ring_full[(seq + 1) % D3_RING], ((seq + 1) / D3_RING) & 1);   // published an item ago
+          mbar_wait3(&sm.ring_full[(seq + 1) % D3_RING], ((seq + 1) / D3_RING) & 1, 5);   // published an item ago
           nxt_frames = nxt.n_frames > 0;
         }
         __syncwarp();
@@ -776,7 +805,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
     const bool clamp_lane = lane < cur_clamp;
     bool ready = false, clamp_loaded = false;
     if (polled) {
-      mbar_wait(&sm.poll_bar[warp], poll_par);
+      mbar_wait3(&sm.poll_bar[warp], poll_par, 6);
       poll_par ^= 1;
       const unsigned int* w = reinterpret_cast<const unsigned int*>(&sm.poll[warp]);
       ready = w[(reinterpret_cast<uintptr_t>(clip_done + cur.c_clip) >> 2) & 3] >= need;
@@ -797,7 +826,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
       if (pend) {
         const Item3& pit = sm.ring[pend_seq % D3_RING];            // (the previous item of the sequence; this one on a second pass)
         const int pend_slot = (n_fft - 1) % P3_RING;
-        mbar_wait(&sm.full[pend_slot], ((n_fft - 1) / P3_RING) & 1);
+        mbar_wait3(&sm.full[pend_slot], ((n_fft - 1) / P3_RING) & 1, 7);
         const bool live = lane < pit.n_frames;
         const float* prow = &sm.P[pend_slot][lane][0];
         // lanes beyond the clip's last frame store to a dump word (stride 0) instead of branching around 16 stores
@@ -837,7 +866,10 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
       if (ld_relaxed_u32(clip_done + cur.c_clip) < need) {
         if (pend) continue;   // run the pending mel phase first
         send_signal(true);
-        while (ld_relaxed_u32(clip_done + cur.c_clip) < need) __nanosleep(2000);
+        for (unsigned int spins = 0; ld_relaxed_u32(clip_done + cur.c_clip) < need; ++spins) {
+          __nanosleep(2000);
+          if (spins > (1u << 22)) mel_wait_timeout(8);   // seconds
+        }
       }
       ready = true;
     }
