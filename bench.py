@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 # DRAM traffic measured once with ncu --set full (profiles/): the bench itself never runs under a profiler
 NCU_GEMM_DRAM_BYTES_PER_STEP = (3.864993 + 0.724993 + 0.777964 + 0.176494 + 0.238801 + 0.016801 + 24 * (
     0.032229 + 0.027745 + 0.053576 + 0.000497 + 0.034340 + 0.050913 + 0.138404 + 0.011794)) * 1e9
-NCU_MEL_DRAM_BYTES_PER_LAUNCH = 516.3e6 + 407.9e6   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02i_mel_v3_summary.txt
+NCU_MEL_DRAM_BYTES_PER_LAUNCH = 516.7e6 + 408.5e6   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02o_mel_v3_final_summary.txt
 
 METRIC = "audio-sec encoded/sec (mel+encoder, 1.7B)"
 UNIT = "audio-s/s"
@@ -535,8 +535,8 @@ def main():
                             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
                             "algorithmic_bytes_per_launch": m["work"] / m["launches"], "avg_launch_ms": (m["ms"] + fin["ms"]) / m["launches"],
                             "workload": "8 x C2 batch (256 x 30 s): 491 MB PCM in, 393 MB log-mel out, >> L2",
-                            # dram__bytes_read.sum 516.3 MB + dram__bytes_write.sum 407.9 MB of one launch on this workload
-                            "traffic": NCU_MEL_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r02i_mel_v3_summary.txt",
+                            # dram__bytes_read.sum 516.7 MB + dram__bytes_write.sum 408.5 MB of one launch on this workload
+                            "traffic": NCU_MEL_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r02o_mel_v3_final_summary.txt",
                             "timing": "per-launch CUDA events on the launching stream, 400 launches back to back before the encoder steps",
                             "sm_mhz": mel_clocks,
                             "audio_s_per_s": 8 * N_CLIPS * CLIP_SECONDS * m["launches"] / ((m["ms"] + fin["ms"]) / 1e3)}

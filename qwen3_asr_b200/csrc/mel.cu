@@ -563,8 +563,10 @@ struct MelRun3 {
     float acc = 0.f;
 #pragma unroll
     for (int j = 0; j < cnt; ++j) acc = fmaf(fw.w[ptr + j], p[lo + j - B0], acc);
-    const float a = fmaxf(acc, 1e-10f);
-    optr[static_cast<long long>(M * ld)] = lg2_fast(a) * 0.30102999566398120f;  // log10; M * ld < 2^31 (checked by the launcher)
+    const float a = acc;
+    // log2 of the mel power, un-clamped and un-scaled (the 1e-10 clamp, the factor log10(2) and the max-8 floor are all applied by the
+    // clamp pass, which rewrites every value anyway): two instructions per filter less, and 4 KB less unrolled code;  M * ld < 2^31
+    optr[static_cast<long long>(M * ld)] = lg2_fast(a);
     // the clip maximum is taken over the clamped power (lg2 is monotone), two filters per FMNMX3
     if constexpr (((M - M0) & 1) != 0) {
       amax = max3(amax, carry, a);
@@ -657,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
       const int s = owe_n % P3_RING;
       if (wait) mbar_wait3(&sm.empty[s], (owe_n / P3_RING) & 1, 2);
       if (lane == 0) {
-        const float vmax = lg2_fast(__uint_as_float(atomicExch(&sm.mel_amax[s], 0u))) * 0.30102999566398120f;
+        const float vmax = lg2_fast(fmaxf(__uint_as_float(atomicExch(&sm.mel_amax[s], 0u)), 1e-10f));   // log2 units, >= log2(1e-10)
         atomicMax(clip_max + owe_clip, float_to_ordered(vmax));
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(clip_done + owe_clip) : "memory");
       }
@@ -874,10 +876,16 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel_v3(const float* __re
       ready = true;
     }
     if (cur_clamp > 0 && clamp_lane) {
-      const float floor_v = ordered_to_float(__float_as_uint(floor_raw)) - 8.0f;
+      // The raw values are log2 of the mel power.  With c = log10(2): log10 = c L, the reference's max(log10, log10max - 8) and its
+      // 1e-10 clamp are max(L, F) with F = max(c Lmax - 8, -10) / c, and (x + 4) / 4 = (max(L, F) - F) * (c / 4) + (floor10 + 4) / 4.
+      // Written relative to the floor so that a clamped value is EXACTLY the reference's (a silent clip: -1.5).
+      const float vmax10 = ordered_to_float(__float_as_uint(floor_raw)) * 0.30102999566398120f;
+      const float floor10 = fmaxf(vmax10 - 8.0f, -10.0f);
+      const float floor_v = floor10 * 3.3219280948873623f;
+      const float floor_out = fmaf(floor10, 0.25f, 1.0f);
       float* p = ctile;
 #pragma unroll
-      for (int i = 0; i < 16; ++i, p += row_stride) __stcg(p, fmaf(fmaxf(c[i], floor_v), 0.25f, 1.0f));   // == (x + 4) / 4 exactly
+      for (int i = 0; i < 16; ++i, p += row_stride) __stcg(p, fmaf(fmaxf(c[i], floor_v) - floor_v, 0.07525749891599530f, floor_out));
     }
     __syncwarp();   // every lane has read the previous item's descriptor (its mel phase ran in this pass)
     if (seq > 0 && lane == 0) mbar_arrive(&sm.ring_empty[(seq - 1) % D3_RING]);

@@ -647,10 +647,12 @@ def test_layernorm_modes_agree(tiny, golden, mode):
         other.close()
 
 
-def test_logmel_kernel_variants_are_bit_identical(tiny, golden, monkeypatch):
+def test_logmel_kernel_variants_agree(tiny, golden, monkeypatch):
     """QASR_MEL=v1 (round 1: CTA-synchronous, ticketed, bulk-copied slabs) and the default v3 (ticketed, warp-autonomous,
-    mbarrier ring of power tiles, clamp tiles riding on later items) run the same arithmetic in the same order: identical bits, on
-    the golden batch, on edge lengths, and on a batch long enough (> 3 grid-strides of items) for clamps to run in flight."""
+    mbarrier ring of power tiles, clamp tiles riding on later items) run the same transform in the same order; v3 keeps log2 of the
+    mel power until its clamp pass applies the factor log10(2), the 1e-10 clamp and the max-8 floor at once (two instructions per
+    filter less), so the two agree to float32 rounding (<= 2e-6 of a feature range of ~2), on the golden batch, on edge lengths,
+    and on a batch long enough (> 4 grid-fulls of items) for clamps to run in flight."""
     from oracle.signals import speech_like
     from qwen3_asr_b200 import B200AudioEncoder
 
@@ -667,6 +669,7 @@ def test_logmel_kernel_variants_are_bit_identical(tiny, golden, monkeypatch):
             a, fa = enc.logmel(clips)
             b, fb = old.logmel(clips)
             torch.cuda.synchronize()
-            assert fa.tolist() == fb.tolist() and torch.equal(a, b)
+            assert fa.tolist() == fb.tolist()
+            assert (a - b).abs().max().item() <= 2e-6, (a - b).abs().max().item()
     finally:
         old.close()
