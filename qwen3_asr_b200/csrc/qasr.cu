@@ -308,19 +308,30 @@ int staging_acquire(qasr_handle_s* h, size_t bytes, Staging** out) {
     s->in_flight = false;
   }
   if (bytes > s->cap) {
-    if (s->host != nullptr) QASR_CUDA_CHECK(cudaFreeHost(s->host));
-    if (s->dev != nullptr) {
-      QASR_CUDA_CHECK(cudaFree(s->dev));
-      h->device_bytes -= s->cap;
-    }
-    s->host = nullptr;
-    s->dev = nullptr;
-    s->cap = 0;
+    // Grow EVERY slot now, not just this one: the slots are handed out round-robin, so a request of a new size class would otherwise
+    // hit a too-small slot on each of the next calls as well -- and every growth is a cudaFree / cudaFreeHost, i.e. a device-wide
+    // synchronisation in the middle of a pipelined stream (seen as one 250 ms step in five on the one-hour workload).
     const size_t want = align_up(bytes + bytes / 2, 1 << 16);
-    QASR_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&s->host), want));
-    QASR_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->dev), want));
-    s->cap = want;
-    h->device_bytes += want;
+    for (int i = 0; i < kStagingSlots; ++i) {
+      Staging* g = &h->staging[i];
+      if (g->cap >= want) continue;
+      if (g->in_flight) {
+        QASR_CUDA_CHECK(cudaEventSynchronize(g->ev));
+        g->in_flight = false;
+      }
+      if (g->host != nullptr) QASR_CUDA_CHECK(cudaFreeHost(g->host));
+      if (g->dev != nullptr) {
+        QASR_CUDA_CHECK(cudaFree(g->dev));
+        h->device_bytes -= g->cap;
+      }
+      g->host = nullptr;
+      g->dev = nullptr;
+      g->cap = 0;
+      QASR_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&g->host), want));
+      QASR_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g->dev), want));
+      g->cap = want;
+      h->device_bytes += want;
+    }
   }
   *out = s;
   return 0;
