@@ -35,8 +35,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # DRAM traffic measured once with ncu --set full (profiles/): the bench itself never runs under a profiler
-NCU_GEMM_DRAM_BYTES_PER_STEP = (3.864993 + 0.724993 + 0.777964 + 0.176494 + 0.238801 + 0.016801 + 24 * (
-    0.032229 + 0.027745 + 0.053576 + 0.000497 + 0.034340 + 0.050913 + 0.138404 + 0.011794)) * 1e9
+# (read + write GB of conv2, conv3, conv_out, then per layer qkv, out_proj, fc1, fc2: profiles/r02p_gemm_raw_summary.txt, final build)
+NCU_GEMM_DRAM_BYTES_PER_STEP = (3.752991 + 0.727449 + 0.779130 + 0.177139 + 0.241481 + 0.020581 + 24 * (
+    0.032237 + 0.028606 + 0.053577 + 0.000636 + 0.034357 + 0.051031 + 0.138782 + 0.013685)) * 1e9
 NCU_MEL_DRAM_BYTES_PER_LAUNCH = 516.7e6 + 408.5e6   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02o_mel_v3_final_summary.txt
 
 METRIC = "audio-sec encoded/sec (mel+encoder, 1.7B)"
@@ -521,7 +522,7 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of the family's 101 launches of one C2 step (conv2 4.59 GB, conv3 0.95 GB,
             # conv_out 0.26 GB, per layer qkv 60 MB + out_proj 54 MB + fc1 85 MB + fc2 150 MB), ncu --set full, divided by 101
             "traffic": NCU_GEMM_DRAM_BYTES_PER_STEP / 101.0 if args.config == "c2" and args.quantize is None else None,
-            "traffic_source": "profiles/r02g_gemm_raw_summary.txt (one ncu --set full capture of each kernel of the family, C2 batch)",
+            "traffic_source": "profiles/r02p_gemm_raw_summary.txt (one ncu --set full capture of each kernel of the family, C2 batch, final build)",
         }
         kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                        "tflops": (v["work"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and k != "logmel" and v["work"] > 0 else None}
