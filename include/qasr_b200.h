@@ -109,6 +109,15 @@ QASR_API int64_t qasr_token_len(int64_t feature_len);
  * returns the number of floats written, or a negative value if capacity is too small / the library's exhaustive self-check fails. */
 QASR_API int qasr_gelu_table(float* table_out, int capacity);
 
+/* The work list the log-mel kernel walks for a batch (host-only entry point, no GPU needed; csrc/mel.cuh Item3): item i = the i-th
+ * 32-frame tile to transform, clip by clip, plus the 32-frame tile whose max-8 clamp it carries -- a tile of a clip whose last
+ * frame item lies at least 8 * num_sms items earlier (FIFO), so that the clamp finds the clip maximum final and the tile still in
+ * L2; tiles left over ride on trailing items without frames.  Writes 8 int64 per item (clip, frame0, n_frames, col0, clamp clip,
+ * clamp frame0, clamp n_frames, frame items of the clamp's clip) when items_out is not NULL; returns the item count, -1 on a bad
+ * argument.  Replaces nothing in the reference (WhisperFeatureExtractor clamps after the whole clip, feature_extraction_whisper.py:
+ * 160-163); it exists so that the scheduling invariants of the kernel are testable on the CPU. */
+QASR_API int64_t qasr_mel_plan(const int64_t* clip_offsets, int n_clips, int num_sms, int64_t* items_out, int64_t capacity_items);
+
 /* Log-mel of n_clips mono 16 kHz float32 clips packed back to back on the device
  * (replaces WhisperFeatureExtractor._torch_extract_fbank_features per clip, standalone semantics).
  *   pcm_dev            float32, clip i = samples [clip_offsets[i], clip_offsets[i+1])  (host int64 [n_clips+1])

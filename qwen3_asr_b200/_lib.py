@@ -71,6 +71,7 @@ SIGNATURES = {
     "qasr_pool_submit": (C.c_int, [_P, _P, _I64P, C.c_int, _P, C.c_int64, _I64P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "qasr_pool_collect": (C.c_int, [_P, C.c_uint64]),
     "qasr_gelu_table": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
+    "qasr_mel_plan": (C.c_int64, [_I64P, C.c_int, C.c_int, _I64P, C.c_int64]),
     "qasr_pool_plan": (C.c_int, [_I64P, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "qasr_pool_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int, C.c_int]),
     "qasr_pool_set_sharding": (C.c_int, [_P, C.c_int]),

@@ -999,6 +999,73 @@ int qasr_gelu_table(float* table_out, int capacity) {
 
 size_t qasr_workspace_bytes(qasr_handle_t h) { return h == nullptr ? 0 : h->device_bytes; }
 
+namespace {
+size_t mel_v3_tiles(const int64_t* clip_offsets, int n_clips) {
+  size_t n_tiles = 0;
+  for (int i = 0; i < n_clips; ++i) n_tiles += static_cast<size_t>(((clip_offsets[i + 1] - clip_offsets[i]) / mel::HOP + mel::FB - 1) / mel::FB);
+  return n_tiles;
+}
+// The work list of logmel_kernel_v3 (host-only; qasr_mel_plan exposes it to the CPU tests).  `items` holds 2 x mel_v3_tiles entries;
+// returns the number written.
+size_t build_mel_items_v3(const int64_t* clip_offsets, int n_clips, int num_sms, mel::Item3* items) {
+  const size_t lag = static_cast<size_t>(mel::v3_clamp_lag(num_sms));
+  struct Tile { int clip, frame0, n_frames, need; long long col0; size_t eligible_at; };
+  std::vector<Tile> queue;
+  queue.reserve(mel_v3_tiles(clip_offsets, n_clips));
+  size_t q_head = 0, ni = 0;
+  long long col = 0;
+  auto attach_clamp = [&](mel::Item3& it, size_t index) {
+    if (q_head < queue.size() && queue[q_head].eligible_at <= index) {
+      const Tile& t = queue[q_head++];
+      it.c_clip = t.clip; it.c_frame0 = t.frame0; it.c_n_frames = t.n_frames; it.c_need = t.need; it.c_col0 = t.col0;
+    } else {
+      it.c_clip = 0; it.c_frame0 = 0; it.c_n_frames = 0; it.c_need = 0; it.c_col0 = 0;
+    }
+    it.pad_ = 0;
+  };
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
+    const int t = static_cast<int>(n / mel::HOP);
+    const int need = (t + mel::FB - 1) / mel::FB;
+    for (int f0 = 0; f0 < t; f0 += mel::FB) {
+      mel::Item3& it = items[ni];
+      it.clip = i; it.frame0 = f0; it.n_frames = std::min(mel::FB, t - f0); it.n_samples = static_cast<int>(n);
+      it.pcm_off = clip_offsets[i]; it.col0 = col;
+      attach_clamp(it, ni);
+      ++ni;
+    }
+    for (int f0 = 0; f0 < t; f0 += mel::FB) queue.push_back({i, f0, std::min(mel::FB, t - f0), need, col, ni - 1 + lag});
+    col += t;
+  }
+  while (q_head < queue.size()) {
+    mel::Item3& it = items[ni];
+    it.clip = 0; it.frame0 = 0; it.n_frames = 0; it.n_samples = 0; it.pcm_off = 0; it.col0 = 0;
+    const Tile& t = queue[q_head++];   // nothing left to wait behind: the kernel waits for the clip if it has to
+    it.c_clip = t.clip; it.c_frame0 = t.frame0; it.c_n_frames = t.n_frames; it.c_need = t.need; it.c_col0 = t.col0; it.pad_ = 0;
+    ++ni;
+  }
+  return ni;
+}
+}  // namespace
+
+int64_t qasr_mel_plan(const int64_t* clip_offsets, int n_clips, int num_sms, int64_t* items_out, int64_t capacity_items) {
+  if (clip_offsets == nullptr || n_clips < 0 || num_sms < 1) return -1;
+  for (int i = 0; i < n_clips; ++i)
+    if (clip_offsets[i + 1] < clip_offsets[i] || clip_offsets[i + 1] - clip_offsets[i] >= (1LL << 31)) return -1;
+  std::vector<mel::Item3> items(2 * mel_v3_tiles(clip_offsets, n_clips) + 1);
+  const size_t ni = build_mel_items_v3(clip_offsets, n_clips, num_sms, items.data());
+  if (items_out != nullptr) {
+    if (static_cast<int64_t>(ni) > capacity_items) return -1;
+    for (size_t i = 0; i < ni; ++i) {
+      const mel::Item3& it = items[i];
+      int64_t* o = items_out + 8 * i;
+      o[0] = it.clip; o[1] = it.frame0; o[2] = it.n_frames; o[3] = it.col0;
+      o[4] = it.c_clip; o[5] = it.c_frame0; o[6] = it.c_n_frames; o[7] = it.c_need;
+    }
+  }
+  return static_cast<int64_t>(ni);
+}
+
 int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offsets, int n_clips, float* mel_out_dev, int64_t mel_ld,
                 int64_t* feature_lens_out, void* stream_v) {
   QASR_REQUIRE(h != nullptr && clip_offsets != nullptr && n_clips >= 0, "qasr_logmel: bad argument");
@@ -1038,47 +1105,10 @@ int qasr_logmel(qasr_handle_t h, const float* pcm_dev, const int64_t* clip_offse
     // least `lag` items earlier (FIFO; still L2-resident unless one clip is longer than the lag).  The tiles left over at the end
     // ride on items without frames.  Items are claimed in list order (ticket), so everything a clamp waits for has a smaller
     // ticket, i.e. is finished or held by a running CTA: no deadlock for any grid size.
-    size_t n_tiles = 0;
-    for (int i = 0; i < n_clips; ++i) n_tiles += static_cast<size_t>(((clip_offsets[i + 1] - clip_offsets[i]) / mel::HOP + mel::FB - 1) / mel::FB);
-    const size_t lag = static_cast<size_t>(mel::v3_clamp_lag(h->num_sms));
+    const size_t n_tiles = mel_v3_tiles(clip_offsets, n_clips);
     const size_t total = 2 * n_tiles * sizeof(mel::Item3);   // upper bound: every tile clamped by an item of its own
     if (staging_acquire(h, total, &st) != 0) return 2;
-    mel::Item3* items = reinterpret_cast<mel::Item3*>(st->host);
-    struct Tile { int clip, frame0, n_frames, need; long long col0; size_t eligible_at; };
-    std::vector<Tile> queue;
-    queue.reserve(n_tiles);
-    size_t q_head = 0, ni = 0;
-    long long col = 0;
-    auto attach_clamp = [&](mel::Item3& it, size_t index) {
-      if (q_head < queue.size() && queue[q_head].eligible_at <= index) {
-        const Tile& t = queue[q_head++];
-        it.c_clip = t.clip; it.c_frame0 = t.frame0; it.c_n_frames = t.n_frames; it.c_need = t.need; it.c_col0 = t.col0;
-      } else {
-        it.c_clip = 0; it.c_frame0 = 0; it.c_n_frames = 0; it.c_need = 0; it.c_col0 = 0;
-      }
-      it.pad_ = 0;
-    };
-    for (int i = 0; i < n_clips; ++i) {
-      const int64_t n = clip_offsets[i + 1] - clip_offsets[i];
-      const int t = static_cast<int>(n / mel::HOP);
-      const int need = (t + mel::FB - 1) / mel::FB;
-      for (int f0 = 0; f0 < t; f0 += mel::FB) {
-        mel::Item3& it = items[ni];
-        it.clip = i; it.frame0 = f0; it.n_frames = std::min(mel::FB, t - f0); it.n_samples = static_cast<int>(n);
-        it.pcm_off = clip_offsets[i]; it.col0 = col;
-        attach_clamp(it, ni);
-        ++ni;
-      }
-      for (int f0 = 0; f0 < t; f0 += mel::FB) queue.push_back({i, f0, std::min(mel::FB, t - f0), need, col, ni - 1 + lag});
-      col += t;
-    }
-    while (q_head < queue.size()) {
-      mel::Item3& it = items[ni];
-      it.clip = 0; it.frame0 = 0; it.n_frames = 0; it.n_samples = 0; it.pcm_off = 0; it.col0 = 0;
-      const Tile& t = queue[q_head++];   // nothing left to wait behind: the kernel waits for the clip if it has to
-      it.c_clip = t.clip; it.c_frame0 = t.frame0; it.c_n_frames = t.n_frames; it.c_need = t.need; it.c_col0 = t.col0; it.pad_ = 0;
-      ++ni;
-    }
+    const size_t ni = build_mel_items_v3(clip_offsets, n_clips, h->num_sms, reinterpret_cast<mel::Item3*>(st->host));
     QASR_CUDA_CHECK(cudaMemcpyAsync(st->dev, st->host, ni * sizeof(mel::Item3), cudaMemcpyHostToDevice, stream));
     QASR_LAUNCH(h, "logmel", mel_bytes, stream,
                 launch_logmel_v3(pcm_dev, reinterpret_cast<const mel::Item3*>(st->dev), static_cast<int>(ni), h->mel_tables, h->mel_tables_host,

@@ -173,6 +173,43 @@ def test_gelu_table_is_the_correctly_rounded_erf_gelu(lib):
     assert tab[0, 0] == 0.5 and tab[1, 0] == 0.5 and tab[0, -1] == 1.0 and tab[1, -1] == 0.0
 
 
+def test_logmel_work_list_invariants(lib):
+    """qasr_mel_plan (host-only): the list logmel_kernel_v3 walks.  Every 32-frame tile is transformed exactly once, in clip order, and
+    clamped exactly once; a clamp rides at least `lag` = 8 x SMs items behind the LAST frame item of its clip (everything it waits for
+    has a smaller ticket: no deadlock, and the clip maximum is final); `need` counts the clip's frame items; empty clips vanish."""
+    import ctypes as C
+
+    rng = np.random.default_rng(7)
+    for n_sms, lens in ((148, [480000] * 32), (148, [0, 201, 80000, 0, 16000 * 30 + 77, 320, 7200]), (4, list(rng.integers(161, 200000, 40))),
+                        (148, [16000 * 3600]), (2, [])):
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        n = lib.qasr_mel_plan(offs.ctypes.data_as(C.POINTER(C.c_int64)), len(lens), n_sms, None, 0)
+        buf = np.zeros((max(n, 1), 8), dtype=np.int64)
+        assert lib.qasr_mel_plan(offs.ctypes.data_as(C.POINTER(C.c_int64)), len(lens), n_sms, buf.ctypes.data_as(C.POINTER(C.c_int64)), n) == n
+        items = buf[:n]
+        frames = [int(x) // 160 for x in lens]
+        tiles = [(c, f0, min(32, t - f0)) for c, t in enumerate(frames) for f0 in range(0, t, 32)]
+        fr = [(int(i[0]), int(i[1]), int(i[2])) for i in items if i[2] > 0]
+        assert fr == tiles                                                     # transformed once, in order
+        cl = sorted((int(i[4]), int(i[5]), int(i[6])) for i in items if i[6] > 0)
+        assert cl == sorted(tiles)                                             # clamped once
+        col0 = np.concatenate([[0], np.cumsum(frames)])
+        last = {}
+        for k, i in enumerate(items):
+            if i[2] > 0:
+                last[int(i[0])] = k
+                assert i[3] == col0[int(i[0])]
+        lag = 8 * n_sms
+        n_frame_items = len(tiles)
+        for k, i in enumerate(items):
+            if i[6] > 0:
+                c = int(i[4])
+                assert i[7] == (frames[c] + 31) // 32                          # need = frame items of the clip
+                assert k > last[c]                                             # its clip's last frame item has a smaller ticket ...
+                assert k >= min(last[c] + lag, n_frame_items)                  # ... by at least the lag, or it rides at the tail
+        assert n <= 2 * len(tiles)
+
+
 def test_pool_sharding_rule_on_the_host(lib):
     """qasr_pool_plan = the rule qasr_pool_submit shards by: contiguous clip ranges, near-equal mel-frame counts, every clip placed,
     empty ranges only when there are fewer clips than devices.  Pure host code: runs without a GPU."""
