@@ -439,7 +439,8 @@ __global__ void __launch_bounds__(THREADS, 2) logmel_kernel(const float* __restr
 }
 
 // ===========================================================================================================================
-// v3 (round 2, the default; QASR_MEL=v1 selects the kernel above): the same arithmetic, re-scheduled so that NO warp ever waits
+// v3 (round 2, the default; QASR_MEL=v1 selects the kernel above): the same transform (results equal to float32 rounding: v3 keeps
+// log2 of the mel power until its clamp pass applies log10(2), the 1e-10 clamp and the max-8 floor at once), re-scheduled so that NO warp ever waits
 // at a CTA-wide barrier.  ncu on v1: 35 % issue utilisation, 4.75 barrier-stall cycles per issued instruction (three
 // __syncthreads per 32-frame item at 16 warps per SM).  Here
 //   * items are still claimed through the global ticket (a static i -> CTA i mod grid assignment let CTAs drift apart and spin on

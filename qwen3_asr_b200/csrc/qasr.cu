@@ -137,7 +137,7 @@ struct qasr_handle_s {
   size_t ln_acc_rows = 0;
   CUtensorMap tm_x;
   bool keep_debug = false;  // QASR_DEBUG_KEEP=1: keep a copy of the post-conv_out embeddings
-  int mel_variant = 3;      // QASR_MEL=v1: the CTA-synchronous, ticketed log-mel kernel of round 1 (bit-identical to the default v3)
+  int mel_variant = 3;      // QASR_MEL=v1: the CTA-synchronous, ticketed log-mel kernel of round 1 (equal to the default v3 to float32 rounding)
   bool use_graph = true;    // QASR_GRAPH=0: launch every kernel eagerly even for small batches (A/B, debugging)
   int chunks_per_window = 8;
   int attn_tile_rows = 128;  // token rows of the attention kernel's TMA tiles (112 when every window fits)
